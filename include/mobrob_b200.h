@@ -1,0 +1,116 @@
+/* libmobrob_b200.so -- C ABI of the B200-native goal-conditioned PPO hot path.
+ *
+ * The reference (ZikangXiong/mobrob) is pure Python and has no FFI of its own: its
+ * boundaries are three Python protocols (EnvWrapper, SB3 VecEnv, SB3 PPO).  The host
+ * layer in mobrob_b200/ mirrors those protocols and binds this library with ctypes
+ * (INTEGRATION.md shows the stub).  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout; [SB3]/[GYM]/[MJ]
+ * are its un-vendored dependencies stable-baselines3 2.0.0 / gymnasium 0.28.1 /
+ * MuJoCo 2.1.0).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the handle's device unless its name starts
+ *     with h_ (host); buffers are caller-owned (torch tensors on the Python side) and
+ *     only borrowed for the duration of the stream-ordered call;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - return 0 on success, a negative mr_status otherwise; mr_last_error() gives the
+ *     message (thread local); nothing throws or aborts;
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef MOBROB_B200_H
+#define MOBROB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MR_OK = 0,
+    MR_ERR_ARG = -1,
+    MR_ERR_CUDA = -2,
+    MR_ERR_ALLOC = -3,
+    MR_ERR_UNSUPPORTED = -4
+} mr_status;
+
+enum { MR_ENV_POINT = 0, MR_ENV_CAR = 1 };
+
+typedef struct mr_env mr_env;
+
+int mr_version(void);
+const char* mr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+uint64_t mr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Batched goal environment.  Replaces, for N environments at once,
+ *   EnvWrapper.__init__/build_env        src/mobrob/envs/wrapper.py:16-37, 238-242
+ *   get_env(..., terminate_on_goal, time_limit) + [GYM] TimeLimit   wrapper.py:549-571
+ *   [SB3] make_vec_env / Monitor / DummyVecEnv   src/mobrob/rl_control/ppo.py:37-48
+ * kind: MR_ENV_POINT (xmls/point.xml) or MR_ENV_CAR (xmls/car.xml).
+ * time_limit <= 0 means no TimeLimit wrapper (examples/control.py semantics). */
+int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int terminate_on_goal,
+                  mr_env** out);
+void mr_env_destroy(mr_env* env);
+int mr_env_obs_dim(const mr_env* env);   /* point 14, car 26 (engine.py:420-567) */
+int mr_env_state_dim(const mr_env* env); /* doubles per env in get/set_state */
+
+/* EnvWrapper.seed (wrapper.py:95-107) for every env: the two gymnasium Box streams
+ * (init_space -> PCG64(SeedSequence(s)), goal_space -> PCG64(SeedSequence(s + 1))) arrive as
+ * raw PCG64 words [N][4] = (state_hi, state_lo, inc_hi, inc_lo); engine_seed [N] is
+ * Engine._seed (engine.py:629-631).  Host pointers, copied before returning. */
+int mr_env_seed(mr_env* env, const uint64_t* h_pcg_init, const uint64_t* h_pcg_goal,
+                const int64_t* h_engine_seed, void* stream);
+
+/* EnvWrapper.reset (wrapper.py:173-201) for the envs with mask[i] != 0 (mask NULL = all).
+ * first != 0 forces the full robot reset of the first call (wrapper.py:182); otherwise the
+ * robot is re-placed only when the goal is not reached.  Samples come from the seeded
+ * reference streams on the device.  obs_out [N][O] float32 rows are written for masked envs. */
+int mr_env_reset(mr_env* env, const uint8_t* mask, int first, float* obs_out, void* stream);
+
+/* [SB3] VecEnv.step_wait over EnvWrapper.step (wrapper.py:156-171), Engine.step
+ * (engine.py:1392-1464: clip, 10 x mj_step, mj_forward), reward_fn (wrapper.py:137-154),
+ * reached (wrapper.py:203-207), TimeLimit, Monitor and the auto-reset.
+ *   act      [N][2] f32 in     obs      [N][O] f32 out (post-reset row where done)
+ *   rew      [N] f32 out       done     [N] u8 out
+ *   trunc    [N] u8 out        (= info["TimeLimit.truncated"])
+ *   term_obs [N][O] f32 out    (= info["terminal_observation"], written where done; may be NULL)
+ *   ep_ret   [N] f64 out, ep_len [N] i32 out (= info["episode"] r / l, valid where done; may be NULL) */
+int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* done,
+                uint8_t* trunc, float* term_obs, double* ep_ret, int32_t* ep_len, void* stream);
+
+/* EnvWrapper.get_obs (wrapper.py:272-273 -> Engine.obs, engine.py:1174-1263). */
+int mr_env_get_obs(mr_env* env, float* obs_out, void* stream);
+/* Reference-view state, [N][state_dim] float64.
+ * point: qpos(3) qvel(3) body_pos_xy(2) start_heading(1) ctrl(2) goal_xy(2) elapsed(1) ep_ret(1) */
+int mr_env_get_state(mr_env* env, double* state_out, void* stream);
+int mr_env_set_state(mr_env* env, const double* state_in, void* stream);
+/* EnvWrapper.get_pos (wrapper.py:269-270): world xy, [N][2] float64. */
+int mr_env_get_pos(mr_env* env, double* pos_out, void* stream);
+/* counters for tests: [N][2] int32 = (#resets, #full resets) */
+int mr_env_get_reset_counts(mr_env* env, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Policy.  Replaces [SB3] ActorCriticPolicy("MlpPolicy") forward / predict_values /
+ * predict(deterministic=True) (call sites ppo.py:50-59, examples/control.py:39).
+ * params: the 13 state-dict tensors of the shipped zips flattened in state-dict order
+ * (log_std, policy_net.0.w/b, policy_net.2.w/b, value_net.0.w/b, value_net.2.w/b,
+ * action_net.w/b, value_net.w/b): 10437 floats for O=14, 11973 for O=26.
+ *   eps  [n][2] f32 standard normal draws, or NULL for the deterministic mean
+ *   act  [n][2] f32 out (unclipped: mu + exp(log_std) * eps, or mu)
+ *   logp [n] f32 out (may be NULL), val [n] f32 out (may be NULL) */
+int mr_policy_forward(const float* params, int obs_dim, const float* obs, const float* eps,
+                      float* act, float* logp, float* val, int64_t n, void* stream);
+
+/* [SB3] RolloutBuffer.compute_returns_and_advantage in numpy's exact dtype flow (float32 deltas,
+ * float64 running advantage, no FMA) -- bit-identical to the numpy loop.
+ * All arrays [T][N] f32 time-major; last_val [N] f32, last_done [N] u8. */
+int mr_gae(const float* rew, const float* val, const float* ep_start, const float* last_val,
+           const uint8_t* last_done, double gamma, double lam, float* adv, float* ret, int64_t T,
+           int64_t N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBROB_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of libmobrob_b200.so (include/mobrob_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling
+into it without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+from . import build as _build
+
+_LIB = None
+
+_P = c_void_p
+
+_SIGNATURES = {
+    "mr_version": (c_int, []),
+    "mr_last_error": (c_char_p, []),
+    "mr_launch_count": (c_uint64, []),
+    "mr_env_create": (c_int, [c_int, c_int64, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "mr_env_destroy": (None, [_P]),
+    "mr_env_obs_dim": (c_int, [_P]),
+    "mr_env_state_dim": (c_int, [_P]),
+    "mr_env_seed": (c_int, [_P, _P, _P, _P, _P]),
+    "mr_env_reset": (c_int, [_P, _P, c_int, _P, _P]),
+    "mr_env_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mr_env_get_obs": (c_int, [_P, _P, _P]),
+    "mr_env_get_state": (c_int, [_P, _P, _P]),
+    "mr_env_set_state": (c_int, [_P, _P, _P]),
+    "mr_env_get_pos": (c_int, [_P, _P, _P]),
+    "mr_env_get_reset_counts": (c_int, [_P, _P, _P]),
+    "mr_policy_forward": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    "mr_gae": (c_int, [_P, _P, _P, _P, _P, c_double, c_double, _P, _P, c_int64, c_int64, _P]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/mobrob_b200.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen the library (building it first if sources are newer) and declare signatures."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: run `python -m mobrob_b200.build` (or __graft_entry__.build()). "
+            "mobrob_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class MobrobError(RuntimeError):
+    pass
+
+
+def check(status: int):
+    if status != 0:
+        raise MobrobError(f"libmobrob_b200 error {status}: {load().mr_last_error().decode()}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array, None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def launch_count() -> int:
+    return int(load().mr_launch_count())

@@ -1,0 +1,124 @@
+// Point robot: MuJoCo 2.1.0 mj_step on xmls/point.xml, written from scratch for one
+// thread per environment with the whole state in fp64 registers.
+//
+// Reference: src/mobrob/envs/mujoco_robots/xmls/point.xml:1-40 (model),
+// engine.py:1392-1464 (Engine.step), engine.py:1174-1263 + 1059-1082 (Engine.obs / compass).
+//
+// The reference integrates slide-x / slide-y in the frame rotated by the start heading psi0
+// and a hinge angle theta on top.  The dynamics are invariant under that fixed rotation
+// (both slides share one damping coefficient), so the device state is kept directly in the
+// world frame: position p = body_pos + R(psi0) q, velocity v = R(psi0) qdot, heading
+// psi = psi0 + theta.  body_pos / psi0 are only needed to export the reference view.
+#pragma once
+
+#include "common.cuh"
+
+namespace mr {
+namespace point {
+
+constexpr double PI = 3.141592653589793;
+constexpr double H = 0.002;          // point.xml:3
+constexpr int FRAME_SKIP = 10;       // engine.py:293-295
+constexpr double R_SPHERE = 0.1;     // point.xml:19
+constexpr double HALF_BOX = 0.05;    // point.xml:20
+constexpr double BOX_X = 0.1;        // point.xml:20
+constexpr double D_SLIDE = 0.01;     // point.xml:16-17
+constexpr double D_HINGE = 0.005;    // point.xml:18
+constexpr double GEAR = 0.3;         // point.xml:37-38
+constexpr double FLIM = 0.05;        // point.xml:7-8
+constexpr double GRAV = 9.81;
+constexpr double MAG_Y = -0.5;       // MuJoCo default magnetic field (0, -0.5, 0)
+
+constexpr double M_SPHERE = 4.0 / 3.0 * PI * (R_SPHERE * R_SPHERE * R_SPHERE);  // density 1
+constexpr double M_BOX = (2 * HALF_BOX) * (2 * HALF_BOX) * (2 * HALF_BOX);
+constexpr double MASS = M_SPHERE + M_BOX;
+constexpr double COM = M_BOX * BOX_X / MASS;
+constexpr double I_O = 0.4 * M_SPHERE * R_SPHERE * R_SPHERE +
+                       M_BOX / 12.0 * 2 * (2 * HALF_BOX) * (2 * HALF_BOX) + M_BOX * BOX_X * BOX_X;
+constexpr double MC = MASS * COM;
+
+constexpr int OBS = 14;
+
+struct Dyn {
+    double px, py, psi, vx, vy, om;
+};
+
+__device__ __forceinline__ double clampd(double x, double lo, double hi) {
+    return fmin(fmax(x, lo), hi);
+}
+
+// (M + h D)^-1 (Q_act - D qdot - C) by the Schur complement on the hinge (B^2 + C^2 = (mc)^2
+// is constant, so both pivots are compile-time constants).  c, s = cos/sin of the heading.
+template <bool IMPLICIT>
+__device__ __forceinline__ void accel(double c, double s, double vx, double vy, double om,
+                                      double f, double cz, double& ax, double& ay, double& al) {
+    constexpr double h = IMPLICIT ? H : 0.0;
+    constexpr double A = MASS + h * D_SLIDE;
+    constexpr double DTH = I_O + h * D_HINGE;
+    constexpr double SCHUR = DTH - MC * MC / A;
+    double tau = GEAR * clampd(cz - GEAR * om, -FLIM, FLIM);  // velocity servo, kv = 1
+    double w2 = om * om;
+    double r0 = f * c - D_SLIDE * vx + MC * c * w2;
+    double r1 = f * s - D_SLIDE * vy + MC * s * w2;
+    double r2 = tau - D_HINGE * om;
+    double t = MC * (-s * r0 + c * r1) / A;
+    al = (r2 - t) / SCHUR;
+    ax = (r0 + MC * s * al) / A;
+    ay = (r1 - MC * c * al) / A;
+}
+
+// Engine.step physics: ctrl already clipped to [-1, 1].
+__device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
+    const double f = GEAR * clampd(cx, -FLIM, FLIM);  // site motor along body x
+#pragma unroll 1
+    for (int k = 0; k < FRAME_SKIP; ++k) {
+        double s, c;
+        sincos(d.psi, &s, &c);
+        double ax, ay, al;
+        accel<true>(c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
+        d.vx += H * ax;
+        d.vy += H * ay;
+        d.om += H * al;
+        d.px += H * d.vx;
+        d.py += H * d.vy;
+        d.psi += H * d.om;
+    }
+}
+
+// Engine.obs(): mj_forward at the current state with the current ctrl; sorted-key layout
+// [accelerometer 0:3 | goal_compass 3:5 | gyro 5:8 | magnetometer 8:11 | velocimeter 11:14].
+__device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
+                                        float* o) {
+    const double f = GEAR * clampd(cx, -FLIM, FLIM);
+    double s, c;
+    sincos(d.psi, &s, &c);
+    double ax, ay, al;
+    accel<false>(c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
+    o[0] = (float)(c * ax + s * ay);
+    o[1] = (float)(-s * ax + c * ay);
+    o[2] = (float)GRAV;
+    double dx = (double)gx - d.px, dy = (double)gy - d.py;
+    double ex = c * dx + s * dy, ey = -s * dx + c * dy;
+    double inv = 1.0 / (sqrt(ex * ex + ey * ey) + 0.001);
+    o[3] = (float)(ex * inv);
+    o[4] = (float)(ey * inv);
+    o[5] = 0.f;
+    o[6] = 0.f;
+    o[7] = (float)d.om;
+    o[8] = (float)(s * MAG_Y);
+    o[9] = (float)(c * MAG_Y);
+    o[10] = 0.f;
+    o[11] = (float)(c * d.vx + s * d.vy);
+    o[12] = (float)(-s * d.vx + c * d.vy);
+    o[13] = 0.f;
+}
+
+// ||a - b|| exactly as numpy evaluates it on two-vectors (no contraction): the reached flag
+// and the reward must not depend on the compiler's FMA choices.
+__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
+    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+}  // namespace point
+}  // namespace mr

@@ -1,0 +1,135 @@
+"""CUDA point environment vs the CPU oracle on the same seeds and actions (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import point_oracle as po, ref_rng
+from oracle.vec_oracle import GoalVecOracle
+
+pytestmark = pytest.mark.gpu
+
+# tolerance named by BASELINE.json north_star: 1e-5 relative on body state and observations
+RTOL = 1e-5
+ATOL_OBS = 1e-6  # observation entries that are exactly 0 / pass through float32 rounding
+
+
+def _actions(rng, n, t):
+    """bang-bang held for random durations plus un-saturated uniform phases."""
+    if t % 11 == 0:
+        return rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    if t % 13 == 0:
+        return rng.uniform(-0.06, 0.06, (n, 2)).astype(np.float32)
+    return np.sign(rng.standard_normal((n, 2))).astype(np.float32) * rng.choice([1.0, 1.7], (n, 2)).astype(np.float32)
+
+
+def _oracle_state(env: GoalVecOracle):
+    b = env.body
+    return np.concatenate([b.state_vector(), env.goal.astype(np.float64),
+                           env.elapsed[:, None].astype(np.float64), env.ep_ret[:, None]], axis=1)
+
+
+@pytest.mark.parametrize("seed,n,time_limit", [(0, 64, 1000), (7, 33, 60)])
+def test_point_vec_env_matches_oracle(cuda_lib, seed, n, time_limit):
+    from mobrob_b200 import GpuVecEnv
+
+    steps = 1000
+    ora = GoalVecOracle(po.PointBody(n), seed=seed, time_limit=time_limit, terminate_on_goal=True)
+    gpu = GpuVecEnv("point", n, seed=seed, time_limit=time_limit, terminate_on_goal=True)
+    o_ref = ora.reset()
+    o_gpu = gpu.reset()
+    np.testing.assert_allclose(o_gpu, o_ref, rtol=RTOL, atol=ATOL_OBS)
+    st = gpu.get_state().cpu().numpy()
+    np.testing.assert_array_equal(st[:, 6:9], _oracle_state(ora)[:, 6:9])  # init xy, heading: bit exact
+    np.testing.assert_array_equal(st[:, 11:13], ora.goal.astype(np.float64))  # goals: bit exact
+    rng = np.random.default_rng(seed + 100)
+    n_done = n_trunc = 0
+    for t in range(steps):
+        a = _actions(rng, n, t)
+        o_ref, r_ref, d_ref, info = ora.step(a)
+        o_gpu, r_gpu, d_gpu, infos = gpu.step(a)
+        np.testing.assert_array_equal(d_gpu, d_ref, err_msg=f"done flags differ at step {t}")
+        np.testing.assert_allclose(o_gpu, o_ref, rtol=RTOL, atol=ATOL_OBS, err_msg=f"obs step {t}")
+        np.testing.assert_allclose(r_gpu, r_ref, rtol=RTOL, atol=1e-7, err_msg=f"reward step {t}")
+        for i in np.nonzero(d_ref)[0]:
+            n_done += 1
+            n_trunc += int(info["truncated"][i])
+            assert infos[i]["TimeLimit.truncated"] == bool(info["truncated"][i])
+            assert infos[i]["episode"]["l"] == int(info["ep_l"][i])
+            assert abs(infos[i]["episode"]["r"] - info["ep_r"][i]) <= 1e-5 * max(1.0, abs(info["ep_r"][i]))
+            np.testing.assert_allclose(infos[i]["terminal_observation"], info["terminal_obs"][i],
+                                       rtol=RTOL, atol=ATOL_OBS)
+        if t % 100 == 99 or t == steps - 1:
+            st = gpu.get_state().cpu().numpy()
+            ref = _oracle_state(ora)
+            scale = np.maximum(np.abs(ref), 1.0)
+            assert np.max(np.abs(st - ref) / scale) < RTOL, f"state diverged at step {t}"
+            np.testing.assert_array_equal(st[:, 13], ref[:, 13])  # episode step index: bit exact
+    counts = gpu.get_reset_counts().cpu().numpy()
+    np.testing.assert_array_equal(counts[:, 0], ora.n_resets)
+    np.testing.assert_array_equal(counts[:, 1], ora.n_full)
+    assert n_done > 0
+    if time_limit < 1000:
+        assert n_trunc > 0
+
+
+def test_point_contact_free_1000_step_trajectory(cuda_lib):
+    """north_star parity case: 1000-step trajectories, no resets (goal far away, no time limit)."""
+    from mobrob_b200 import GpuVecEnv
+
+    n = 256
+    gpu = GpuVecEnv("point", n, seed=11, time_limit=None, terminate_on_goal=False)
+    gpu.reset()
+    st0 = gpu.get_state().cpu().numpy()
+    body = po.PointBody(n)
+    body.q[:] = st0[:, 0:3]; body.v[:] = st0[:, 3:6]; body.body_xy[:] = st0[:, 6:8]
+    body.psi0[:] = st0[:, 8]; body.ctrl[:] = st0[:, 9:11]
+    goal = st0[:, 11:13].astype(np.float32)
+    rng = np.random.default_rng(5)
+    hold = np.zeros((n, 2), np.int64)
+    a = np.zeros((n, 2), np.float32)
+    for t in range(1000):
+        renew = hold <= 0
+        a = np.where(renew, np.sign(rng.standard_normal((n, 2))), a).astype(np.float32)
+        hold = np.where(renew, rng.integers(1, 51, (n, 2)), hold) - 1
+        body.step(a)
+        o_gpu, _, d, _ = gpu.step(a)
+        assert not d.any()
+        if t % 50 == 49:
+            np.testing.assert_allclose(o_gpu, body.obs(goal), rtol=RTOL, atol=ATOL_OBS)
+    st = gpu.get_state().cpu().numpy()
+    ref = body.state_vector()
+    err = np.abs(st[:, :11] - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < RTOL
+    # the physics really ran: robots moved metres and turned many radians
+    assert np.abs(ref[:, 2]).max() > 5.0 and np.abs(ref[:, 0:2]).max() > 1.0
+
+
+def test_device_rng_streams_match_numpy(cuda_lib):
+    """PCG64 (Box.sample) and MT19937 (Engine heading) restated on the device are bit exact."""
+    from mobrob_b200 import GpuVecEnv
+
+    n, seed = 512, 1234
+    gpu = GpuVecEnv("point", n, seed=seed, time_limit=1, terminate_on_goal=True)
+    gpu.reset()
+    init = [ref_rng.init_box() for _ in range(n)]
+    goal = [ref_rng.goal_box() for _ in range(n)]
+    for i in range(n):
+        init[i].seed(seed + i)
+        goal[i].seed(seed + i + 1)
+    eng = seed + np.arange(n)
+    zero = np.zeros((n, 2), np.float32)
+    for rnd in range(6):
+        st = gpu.get_state().cpu().numpy()
+        eng = eng + 2
+        exp_xy = np.stack([b.sample() for b in init]).astype(np.float64)
+        exp_goal = np.stack([g.sample() for g in goal]).astype(np.float64)
+        exp_head = np.array([ref_rng.engine_heading(int(s)) for s in eng])
+        np.testing.assert_array_equal(st[:, 6:8], exp_xy)
+        np.testing.assert_array_equal(st[:, 11:13], exp_goal)
+        np.testing.assert_array_equal(st[:, 8], exp_head)
+        # time_limit = 1: every step truncates -> full reset unless the new goal is within 0.3 m
+        far = np.linalg.norm(exp_xy - exp_goal, axis=1) > 0.35
+        assert far.all() or rnd > 0
+        gpu.step(zero)
+        if not far.all():
+            break
