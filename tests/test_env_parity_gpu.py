@@ -117,19 +117,25 @@ def test_device_rng_streams_match_numpy(cuda_lib):
         init[i].seed(seed + i)
         goal[i].seed(seed + i + 1)
     eng = seed + np.arange(n)
+    xy = np.zeros((n, 2)); head = np.zeros(n); g = np.zeros((n, 2))
+    full = np.ones(n, bool)
     zero = np.zeros((n, 2), np.float32)
-    for rnd in range(6):
+    n_goal_only = 0
+    for rnd in range(8):
+        for i in range(n):
+            if full[i]:
+                eng[i] += 2
+                xy[i] = init[i].sample()
+                head[i] = ref_rng.engine_heading(int(eng[i]))
+            g[i] = goal[i].sample()
         st = gpu.get_state().cpu().numpy()
-        eng = eng + 2
-        exp_xy = np.stack([b.sample() for b in init]).astype(np.float64)
-        exp_goal = np.stack([g.sample() for g in goal]).astype(np.float64)
-        exp_head = np.array([ref_rng.engine_heading(int(s)) for s in eng])
-        np.testing.assert_array_equal(st[:, 6:8], exp_xy)
-        np.testing.assert_array_equal(st[:, 11:13], exp_goal)
-        np.testing.assert_array_equal(st[:, 8], exp_head)
-        # time_limit = 1: every step truncates -> full reset unless the new goal is within 0.3 m
-        far = np.linalg.norm(exp_xy - exp_goal, axis=1) > 0.35
-        assert far.all() or rnd > 0
+        np.testing.assert_array_equal(st[:, 6:8], xy)
+        np.testing.assert_array_equal(st[:, 8], head)
+        np.testing.assert_array_equal(st[:, 11:13], g)
+        # time_limit = 1 and a zero action on a resting robot: every step ends the episode;
+        # the robot is re-placed unless the goal happens to lie within the reach radius
+        dx = g - xy
+        full = ~(np.sqrt(dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1]) < 0.3)
+        n_goal_only += int((~full).sum())
         gpu.step(zero)
-        if not far.all():
-            break
+    assert n_goal_only > 0

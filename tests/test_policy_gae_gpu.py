@@ -75,8 +75,9 @@ def test_gae_bit_exact(cuda_lib, T, N, lam):
     d = lambda x: torch.as_tensor(x).cuda().contiguous()
     adv = torch.empty((T, N), device="cuda")
     ret = torch.empty((T, N), device="cuda")
-    _lib.check(cuda_lib.mr_gae(d(rew).data_ptr(), d(val).data_ptr(), d(starts).data_ptr(),
-                               d(last_val).data_ptr(), d(dones.astype(np.uint8)).data_ptr(), 0.99, lam,
+    t_rew, t_val, t_st, t_lv, t_dn = d(rew), d(val), d(starts), d(last_val), d(dones.astype(np.uint8))
+    _lib.check(cuda_lib.mr_gae(t_rew.data_ptr(), t_val.data_ptr(), t_st.data_ptr(),
+                               t_lv.data_ptr(), t_dn.data_ptr(), 0.99, lam,
                                adv.data_ptr(), ret.data_ptr(), T, N,
                                torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
