@@ -110,6 +110,60 @@ int mr_gae(const float* rew, const float* val, const float* ep_start, const floa
            const uint8_t* last_done, double gamma, double lam, float* adv, float* ret, int64_t T,
            int64_t N, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * PPO update.  Replaces the inner loop of [SB3] PPO.train + torch autograd +
+ * clip_grad_norm_ + torch.optim.Adam (reference call chain: examples/train.py:42-46 ->
+ * src/mobrob/rl_control/ppo.py:73-74 -> PPO.learn).  Rollout arrays are time-major
+ * [T][N](...) float32 as in RolloutBuffer; perm holds env-major sample ids (n * T + t), i.e.
+ * indices into RolloutBuffer.swap_and_flatten order, int64 like np.random.permutation. */
+int mr_ppo_num_params(int obs_dim);  /* 10437 (point) / 11973 (car) */
+int mr_ppo_grad_stride(int obs_dim); /* floats in a gradient vector incl. the 16-slot stats tail:
+                                        [policy_loss, value_loss, clip_fraction, approx_kl, ...] */
+int mr_ppo_max_parts(void);          /* CTAs mr_ppo_grad may use = rows of `partials` */
+
+/* (sum adv, sum adv^2, count) per minibatch of one epoch's permutation -> stats [n_mb][3] f64.
+ * With several ranks the host all-reduces stats so that normalisation is over the global
+ * minibatch, as PPO.train normalises over the whole minibatch. */
+int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                     int64_t N, int64_t T, double* stats, void* stream);
+
+/* evaluate_actions + loss + analytic backward for one minibatch (perm points at its slice).
+ * mb_stats = the minibatch's (global) stats triple.  rank_share = local count / global count.
+ * partials [mr_ppo_max_parts()][stride] scratch; grad [stride] out: d(loss)/d(params) of this
+ * rank's share (sum over ranks = SB3's gradient) followed by the stats tail. */
+int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
+                const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
+                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
+                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
+                float* partials, float* grad, void* stream);
+
+/* clip_grad_norm_(max_grad_norm) then torch.optim.Adam.step (eps as given; SB3 uses 1e-5).
+ * step: device int64 counter (state["step"]), incremented.  info [8] out (may be NULL):
+ * total grad norm, clip coefficient, step, 0, then grad's stats tail (policy_loss, value_loss,
+ * clip_fraction, approx_kl) so that logging needs no extra copy. */
+int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grad, int n_params,
+                 int64_t* step, float lr, float beta1, float beta2, float eps, float max_grad_norm,
+                 float* info, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused rollout.  Replaces [SB3] OnPolicyAlgorithm.collect_rollouts (n_steps = T) over the
+ * vectorised env, including the time-out bootstrap  reward += gamma * V(terminal_obs),
+ * Monitor's episode statistics and RolloutBuffer.add, in one launch (point env).
+ *   last_obs [N][O], last_starts [N] f32 : in/out, carried between rollouts (_last_obs,
+ *                                          _last_episode_starts)
+ *   obs [T][N][O], act [T][N][2] (unclipped), rew/starts/val/logp [T][N] f32 : RolloutBuffer
+ *   last_val [N] f32, last_done [N] u8   : inputs of compute_returns_and_advantage
+ *   eps [T][N][2] f32 standard-normal draws (parity mode: torch's CPU generator cannot be
+ *        reproduced on the device) or NULL -> Philox4x32-10 keyed (seed; env_offset + n,
+ *        noise_offset + t)
+ *   ep_r [ring_cap] f64, ep_l [ring_cap] i32, ep_count [1] u64 : ring of finished episodes
+ *        (Monitor's info["episode"]), head = *ep_count. */
+int mr_rollout(mr_env* env, const float* params, int64_t T, float* last_obs, float* last_starts,
+               float* obs, float* act, float* rew, float* starts, float* val, float* logp,
+               float* last_val, uint8_t* last_done, const float* eps, uint64_t seed,
+               uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
+               int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

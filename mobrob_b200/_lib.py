@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 from . import build as _build
 
@@ -33,6 +33,16 @@ _SIGNATURES = {
     "mr_env_get_reset_counts": (c_int, [_P, _P, _P]),
     "mr_policy_forward": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "mr_gae": (c_int, [_P, _P, _P, _P, _P, c_double, c_double, _P, _P, c_int64, c_int64, _P]),
+    "mr_ppo_num_params": (c_int, [c_int]),
+    "mr_ppo_grad_stride": (c_int, [c_int]),
+    "mr_ppo_max_parts": (c_int, []),
+    "mr_ppo_adv_stats": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
+    "mr_ppo_grad": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
+                            c_float, c_float, c_float, c_int, c_float, _P, _P, _P]),
+    "mr_rollout": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,
+                           c_uint64, c_int64, c_double, _P, _P, _P, c_int, _P]),
+    "mr_adam_step": (c_int, [_P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float,
+                             _P, _P]),
 }
 
 

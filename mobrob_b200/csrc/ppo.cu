@@ -1,0 +1,601 @@
+// PPO update (K8 + K9): replaces the inner loop of [SB3 2.0.0] PPO.train -- evaluate_actions,
+// per-minibatch advantage normalisation, clipped surrogate, value MSE, entropy bonus,
+// backward, clip_grad_norm_, Adam -- reached in the reference through
+// src/mobrob/rl_control/ppo.py:73-74 (PPOCtrl.learn -> PPO.learn).  No autograd: the
+// gradients of the two 64-64 tanh towers are formed analytically.
+//
+// ppo_grad_kernel: one CTA (8 warps) per 64-sample tile, persistent over tiles.
+//   * forward and backward-data run warp-private on 8 samples per warp, lanes own hidden
+//     units (same micro-GEMM as mlp.cuh), activations live in shared memory as
+//     [tower][unit][sample] with a 68-float row stride (conflict-free for every access below);
+//   * weight gradients are CTA-level register-tiled GEMMs over the tile's 64 samples
+//     (dW2: 4x4x2 accumulators per thread, samples consumed four at a time with LDS.128);
+//   * each CTA writes one partial gradient; ppo_reduce_kernel sums the partials in a fixed
+//     order (deterministic), adam_kernel clips by global norm and applies torch's Adam.
+#include "mlp.cuh"
+
+namespace mr {
+
+constexpr int PG_WARPS = 8;
+constexpr int PG_THREADS = PG_WARPS * 32;
+constexpr int PG_E = 8;                    // samples per warp
+constexpr int PG_S = PG_WARPS * PG_E;      // 64 samples per tile
+constexpr int PG_SP = PG_S + 4;            // padded row stride (floats)
+constexpr int STAT_SLOTS = 16;             // tail of the gradient vector
+// tail layout: 0 policy_loss, 1 value_loss, 2 clip_fraction, 3 approx_kl, 4 sample count
+
+__host__ __device__ inline int grad_stride(int O) { return ((make_layout(O).total + 3) & ~3) + STAT_SLOTS; }
+__host__ __device__ inline int stat_base(int O) { return (make_layout(O).total + 3) & ~3; }
+
+struct GradArgs {
+    const float* params;
+    const float* obs;       // [T][N][O]
+    const float* act;       // [T][N][2]
+    const float* old_logp;  // [T][N]
+    const float* adv;       // [T][N]
+    const float* ret;       // [T][N]
+    const int64_t* perm;    // [mb_size] env-major sample ids (n * T + t)
+    int64_t mb_size;
+    const double* mb_stats; // (sum adv, sum adv^2, count) of the GLOBAL minibatch
+    int64_t N, T;
+    float clip_range, ent_coef, vf_coef;
+    int normalize_adv;
+    float* partials;        // [gridDim.x][grad_stride]
+};
+
+template <int O_PAD>
+__global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int O) {
+    extern __shared__ __align__(16) float smem[];
+    const ParamLayout L = make_layout(O);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- shared memory carve-up ---------------------------------------------------------
+    float* p = smem;
+    SmemW W = stage_weights(p, A.params, O);        p += smem_w_floats(O);
+    float4* w2b = reinterpret_cast<float4*>(p);     p += 8192;   // [u][lane] backward pack
+    float* X = p;                                   p += O_PAD * PG_SP;
+    float* H1 = p;                                  p += 128 * PG_SP;
+    float* H2 = p;                                  p += 128 * PG_SP;   // becomes dZ2
+    float* Z1 = p;                                  p += 128 * PG_SP;   // dZ1
+    float* dOut = p;                                p += PG_S * 4;
+    float* red = p;                                 /* PG_WARPS * 32 * 16 floats */
+    for (int idx = tid; idx < 8192; idx += PG_THREADS) {
+        int u = idx >> 7, r = idx & 127, ln = r >> 2, j = r & 3;
+        int k = ln + ((j & 1) ? 32 : 0);
+        reinterpret_cast<float*>(w2b)[idx] = A.params[((j & 2) ? L.vw2 : L.pw2) + u * HID + k];
+    }
+    for (int idx = tid; idx < O_PAD * PG_SP; idx += PG_THREADS) X[idx] = 0.f;
+    __syncthreads();
+
+    // ---- minibatch constants ----------------------------------------------------------------
+    const double cnt = A.mb_stats[2];
+    float adv_mean = 0.f, adv_std = 1.f;
+    const bool do_norm = A.normalize_adv && cnt > 1.0;
+    if (do_norm) {
+        double m = A.mb_stats[0] / cnt;
+        double var = (A.mb_stats[1] - A.mb_stats[0] * m) / (cnt - 1.0);
+        adv_mean = (float)m;
+        adv_std = (float)sqrt(fmax(var, 0.0));
+    }
+    const float inv_b = (float)(1.0 / cnt);
+    const float sig0 = expf(W.logstd[0]), sig1 = expf(W.logstd[1]);
+
+    // ---- persistent accumulators ---------------------------------------------------------------
+    float gW2[2][4][4];   // [tower][u = tu + 16 i][k = tk + 16 j]
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gW2[a][i][j] = 0.f;
+    constexpr int KH = O_PAD / 2;
+    float gW1[KH];        // tower = tid >> 7, unit = tid & 63, k in [half * KH, half * KH + KH)
+#pragma unroll
+    for (int k = 0; k < KH; ++k) gW1[k] = 0.f;
+    float gb1[4] = {0, 0, 0, 0}, gb2[4] = {0, 0, 0, 0};  // lane-owned units, this warp's samples
+    float gWh[6] = {0, 0, 0, 0, 0, 0};  // aW[0][l], aW[0][l+32], aW[1][l], aW[1][l+32], cW[l], cW[l+32]
+    float g_head = 0.f;   // lane (e, j): d loss / d head bias j
+    float g_ls = 0.f;     // lane (e, j<2): d loss / d log_std j (sample part)
+    float st_pl = 0.f, st_vl = 0.f, st_cf = 0.f, st_kl = 0.f;
+
+    const int tu = tid >> 4, tk = tid & 15;
+    const int w1_tower = tid >> 7, w1_unit = tid & 63, w1_half = (tid >> 6) & 1;
+    const int col0 = warp * PG_E;
+
+    const int64_t n_tiles = (A.mb_size + PG_S - 1) / PG_S;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- gather: this warp's 8 samples ----------------------------------------------------
+        const int64_t s_base = tile * PG_S + col0;
+        int64_t my_row = -1;  // lane e < 8 holds the buffer row of sample e
+        if (lane < PG_E && s_base + lane < A.mb_size) {
+            int64_t id = A.perm[s_base + lane];
+            int64_t n = id / A.T, t = id - n * A.T;
+            my_row = t * A.N + n;
+        }
+        for (int it = 0; it < (PG_E * O + 31) / 32; ++it) {  // warp-uniform trip count (shuffles inside)
+            const int idx = it * 32 + lane;
+            const bool in = idx < PG_E * O;
+            const int e = in ? idx / O : 0, k = idx - e * O;
+            const int64_t row = __shfl_sync(0xffffffffu, my_row, e);
+            if (in) X[k * PG_SP + col0 + e] = row >= 0 ? A.obs[row * O + k] : 0.f;
+        }
+        const int e_of = lane / 3, j_of = lane - 3 * e_of;
+        const int64_t row_e = __shfl_sync(0xffffffffu, my_row, e_of < PG_E ? e_of : 0);
+        const bool live = lane < 3 * PG_E && row_e >= 0;
+        float a_j = 0.f, oldlp = 0.f, adv = 0.f, ret = 0.f;
+        if (live) {
+            if (j_of < 2) a_j = A.act[row_e * 2 + j_of];
+            oldlp = A.old_logp[row_e];
+            adv = A.adv[row_e];
+            ret = A.ret[row_e];
+        }
+        __syncwarp();
+
+        // ---- forward layer 1 -----------------------------------------------------------------------
+        float acc[4][PG_E];
+        {
+            float4 b = W.b1p[lane];
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) { acc[0][e] = b.x; acc[1][e] = b.y; acc[2][e] = b.z; acc[3][e] = b.w; }
+        }
+        for (int k = 0; k < O; ++k) {
+            float4 w = W.w1p[k * 32 + lane];
+            float4 x0 = *reinterpret_cast<const float4*>(X + k * PG_SP + col0);
+            float4 x1 = *reinterpret_cast<const float4*>(X + k * PG_SP + col0 + 4);
+            float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) {
+                acc[0][e] = fmaf(w.x, x[e], acc[0][e]);
+                acc[1][e] = fmaf(w.y, x[e], acc[1][e]);
+                acc[2][e] = fmaf(w.z, x[e], acc[2][e]);
+                acc[3][e] = fmaf(w.w, x[e], acc[3][e]);
+            }
+        }
+        auto row_of = [&](int j) { return (j >> 1) * 64 + lane + ((j & 1) ? 32 : 0); };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* dst = H1 + row_of(j) * PG_SP + col0;
+            reinterpret_cast<float4*>(dst)[0] = make_float4(tanhf(acc[j][0]), tanhf(acc[j][1]), tanhf(acc[j][2]), tanhf(acc[j][3]));
+            reinterpret_cast<float4*>(dst)[1] = make_float4(tanhf(acc[j][4]), tanhf(acc[j][5]), tanhf(acc[j][6]), tanhf(acc[j][7]));
+        }
+        __syncwarp();
+
+        // ---- forward layer 2 -----------------------------------------------------------------------
+        {
+            float4 b = W.b2p[lane];
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) { acc[0][e] = b.x; acc[1][e] = b.y; acc[2][e] = b.z; acc[3][e] = b.w; }
+        }
+#pragma unroll 4
+        for (int k = 0; k < HID; ++k) {
+            float4 w = W.w2p[k * 32 + lane];
+            const float* hp = H1 + k * PG_SP + col0;
+            const float* hv = H1 + (64 + k) * PG_SP + col0;
+            float4 p0 = reinterpret_cast<const float4*>(hp)[0], p1 = reinterpret_cast<const float4*>(hp)[1];
+            float4 v0 = reinterpret_cast<const float4*>(hv)[0], v1 = reinterpret_cast<const float4*>(hv)[1];
+            float a[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float b[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) {
+                acc[0][e] = fmaf(w.x, a[e], acc[0][e]);
+                acc[1][e] = fmaf(w.y, a[e], acc[1][e]);
+                acc[2][e] = fmaf(w.z, b[e], acc[2][e]);
+                acc[3][e] = fmaf(w.w, b[e], acc[3][e]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) acc[j][e] = tanhf(acc[j][e]);  // acc now holds h2
+            float* dst = H2 + row_of(j) * PG_SP + col0;
+            reinterpret_cast<float4*>(dst)[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        }
+        __syncwarp();
+
+        // ---- heads, loss, d loss / d head outputs (lane = 3 e + j) -----------------------------------
+        float head = 0.f;
+        if (lane < 3 * PG_E) {
+            const float* hw = W.headw + j_of * 64;
+            const float* h = H2 + (j_of == 2 ? 64 * PG_SP : 0) + col0 + e_of;
+            float s = W.headb[j_of];
+#pragma unroll 8
+            for (int u = 0; u < HID; ++u) s = fmaf(hw[u], h[u * PG_SP], s);
+            head = s;
+        }
+        float lp_j = 0.f, sig = 1.f, diff = 0.f;
+        if (live && j_of < 2) {
+            sig = j_of == 0 ? sig0 : sig1;
+            lp_j = normal_logprob(a_j, head, sig);
+            diff = __fsub_rn(a_j, head);
+        }
+        // logp = lp(j=0) + lp(j=1), broadcast to the sample's three lanes
+        const int lane0 = 3 * e_of;
+        float lp0 = __shfl_sync(0xffffffffu, lp_j, lane0 < 32 ? lane0 : 0);
+        float lp1 = __shfl_sync(0xffffffffu, lp_j, lane0 + 1 < 32 ? lane0 + 1 : 0);
+        float d_out = 0.f;
+        if (live) {
+            const float logp = __fadd_rn(lp0, lp1);
+            const float log_ratio = logp - oldlp;
+            const float ratio = expf(log_ratio);
+            float adv_n = adv;
+            if (do_norm) adv_n = __fdiv_rn(adv - adv_mean, adv_std + 1e-8f);
+            const float lo = 1.f - A.clip_range, hi = 1.f + A.clip_range;
+            const float pl1 = adv_n * ratio;
+            const float pl2 = adv_n * fminf(fmaxf(ratio, lo), hi);
+            const float g_logp = (pl1 <= pl2) ? -adv_n * ratio * inv_b : 0.f;
+            if (j_of < 2) {
+                const float inv_var = 1.f / (sig * sig);
+                d_out = g_logp * diff * inv_var;                       // d/d mu_j
+                g_ls += g_logp * (diff * diff * inv_var - 1.f);        // d/d log_std_j
+            } else {
+                const float dv = head - ret;
+                d_out = A.vf_coef * 2.f * dv * inv_b;                  // d/d V
+                st_vl += dv * dv;
+                st_pl += -fminf(pl1, pl2);
+                st_cf += (fabsf(ratio - 1.f) > A.clip_range) ? 1.f : 0.f;
+                st_kl += (ratio - 1.f) - log_ratio;
+            }
+            g_head += d_out;
+        }
+        if (lane < 3 * PG_E) dOut[(col0 + e_of) * 4 + j_of] = d_out;
+        __syncwarp();
+
+        // ---- backward through the heads: dZ2 (overwrites H2 in place; acc still holds h2) -------
+        {
+            const float aw00 = W.headw[lane], aw01 = W.headw[lane + 32];
+            const float aw10 = W.headw[64 + lane], aw11 = W.headw[96 + lane];
+            const float cw0 = W.headw[128 + lane], cw1 = W.headw[160 + lane];
+            float dz[4][PG_E];
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) {
+                const float4 d = *reinterpret_cast<const float4*>(dOut + (col0 + e) * 4);
+                const float h0 = acc[0][e], h1 = acc[1][e], h2 = acc[2][e], h3 = acc[3][e];
+                gWh[0] = fmaf(d.x, h0, gWh[0]); gWh[1] = fmaf(d.x, h1, gWh[1]);
+                gWh[2] = fmaf(d.y, h0, gWh[2]); gWh[3] = fmaf(d.y, h1, gWh[3]);
+                gWh[4] = fmaf(d.z, h2, gWh[4]); gWh[5] = fmaf(d.z, h3, gWh[5]);
+                dz[0][e] = (d.x * aw00 + d.y * aw10) * (1.f - h0 * h0);
+                dz[1][e] = (d.x * aw01 + d.y * aw11) * (1.f - h1 * h1);
+                dz[2][e] = d.z * cw0 * (1.f - h2 * h2);
+                dz[3][e] = d.z * cw1 * (1.f - h3 * h3);
+                gb2[0] += dz[0][e]; gb2[1] += dz[1][e]; gb2[2] += dz[2][e]; gb2[3] += dz[3][e];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float* dst = H2 + row_of(j) * PG_SP + col0;
+                reinterpret_cast<float4*>(dst)[0] = make_float4(dz[j][0], dz[j][1], dz[j][2], dz[j][3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(dz[j][4], dz[j][5], dz[j][6], dz[j][7]);
+            }
+        }
+        __syncwarp();
+
+        // ---- backward data: dH1 = dZ2 * W2, dZ1 = dH1 * (1 - h1^2) ---------------------------------
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) acc[j][e] = 0.f;
+#pragma unroll 4
+        for (int u = 0; u < HID; ++u) {
+            float4 w = w2b[u * 32 + lane];
+            const float* dp = H2 + u * PG_SP + col0;
+            const float* dv = H2 + (64 + u) * PG_SP + col0;
+            float4 p0 = reinterpret_cast<const float4*>(dp)[0], p1 = reinterpret_cast<const float4*>(dp)[1];
+            float4 v0 = reinterpret_cast<const float4*>(dv)[0], v1 = reinterpret_cast<const float4*>(dv)[1];
+            float a[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float b[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) {
+                acc[0][e] = fmaf(w.x, a[e], acc[0][e]);
+                acc[1][e] = fmaf(w.y, a[e], acc[1][e]);
+                acc[2][e] = fmaf(w.z, b[e], acc[2][e]);
+                acc[3][e] = fmaf(w.w, b[e], acc[3][e]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* hsrc = H1 + row_of(j) * PG_SP + col0;
+            float4 h0 = reinterpret_cast<const float4*>(hsrc)[0], h1 = reinterpret_cast<const float4*>(hsrc)[1];
+            float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int e = 0; e < PG_E; ++e) {
+                acc[j][e] *= (1.f - h[e] * h[e]);
+                gb1[j] += acc[j][e];
+            }
+            float* dst = Z1 + row_of(j) * PG_SP + col0;
+            reinterpret_cast<float4*>(dst)[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        }
+        __syncthreads();
+
+        // ---- weight gradients over the tile's 64 samples (CTA-level register tiles) ------------------
+#pragma unroll
+        for (int tower = 0; tower < 2; ++tower) {
+            const float* dzb = H2 + tower * 64 * PG_SP;
+            const float* hb = H1 + tower * 64 * PG_SP;
+#pragma unroll 2
+            for (int s4 = 0; s4 < PG_S / 4; ++s4) {
+                float4 dz[4], h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dz[i] = *reinterpret_cast<const float4*>(dzb + (tu + 16 * i) * PG_SP + 4 * s4);
+                    h[i] = *reinterpret_cast<const float4*>(hb + (tk + 16 * i) * PG_SP + 4 * s4);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float g = gW2[tower][i][j];
+                        g = fmaf(dz[i].x, h[j].x, g);
+                        g = fmaf(dz[i].y, h[j].y, g);
+                        g = fmaf(dz[i].z, h[j].z, g);
+                        g = fmaf(dz[i].w, h[j].w, g);
+                        gW2[tower][i][j] = g;
+                    }
+            }
+        }
+        {
+            const float* dzr = Z1 + (w1_tower * 64 + w1_unit) * PG_SP;
+            const float* xb = X + (w1_half * KH) * PG_SP;
+#pragma unroll 2
+            for (int s4 = 0; s4 < PG_S / 4; ++s4) {
+                const float4 dz = *reinterpret_cast<const float4*>(dzr + 4 * s4);
+#pragma unroll
+                for (int k = 0; k < KH; ++k) {
+                    const float4 x = *reinterpret_cast<const float4*>(xb + k * PG_SP + 4 * s4);
+                    gW1[k] = fmaf(dz.x, x.x, gW1[k]);
+                    gW1[k] = fmaf(dz.y, x.y, gW1[k]);
+                    gW1[k] = fmaf(dz.z, x.z, gW1[k]);
+                    gW1[k] = fmaf(dz.w, x.w, gW1[k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write this CTA's partial gradient ------------------------------------------------------
+    float* out = A.partials + (size_t)blockIdx.x * grad_stride(O);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[L.pw2 + (tu + 16 * i) * HID + tk + 16 * j] = gW2[0][i][j];
+            out[L.vw2 + (tu + 16 * i) * HID + tk + 16 * j] = gW2[1][i][j];
+        }
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        int kk = w1_half * KH + k;
+        if (kk < O) out[(w1_tower ? L.vw1 : L.pw1) + w1_unit * O + kk] = gW1[k];
+    }
+    // lane-owned sums: 14 floats per lane per warp -> cross-warp reduction in shared memory
+    {
+        float* r = red + (warp * 32 + lane) * 16;
+        r[0] = gb1[0]; r[1] = gb1[1]; r[2] = gb1[2]; r[3] = gb1[3];
+        r[4] = gb2[0]; r[5] = gb2[1]; r[6] = gb2[2]; r[7] = gb2[3];
+        r[8] = gWh[0]; r[9] = gWh[1]; r[10] = gWh[2]; r[11] = gWh[3]; r[12] = gWh[4]; r[13] = gWh[5];
+    }
+    // per-sample-lane sums (lane = 3 e + j): reduce over e with shuffles (fixed order)
+    auto sum_over_e = [&](float v) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < PG_E; ++e) s += __shfl_sync(0xffffffffu, v, (3 * e + (lane % 3)) & 31);
+        return s;
+    };
+    float s_head = sum_over_e(g_head), s_ls = sum_over_e(g_ls);
+    float s_pl = sum_over_e(st_pl), s_vl = sum_over_e(st_vl), s_cf = sum_over_e(st_cf), s_kl = sum_over_e(st_kl);
+    __shared__ float red2[PG_WARPS][12];
+    if (lane < 3) {
+        red2[warp][lane] = s_head;          // d ab0, d ab1, d cb
+        red2[warp][3 + lane] = s_ls;        // d log_std0, d log_std1, (unused)
+    }
+    if (lane == 2) { red2[warp][6] = s_pl; red2[warp][7] = s_vl; red2[warp][8] = s_cf; red2[warp][9] = s_kl; }
+    __syncthreads();
+    for (int it = tid; it < 32 * 14; it += PG_THREADS) {
+        int ln = it / 14, q = it - ln * 14;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < PG_WARPS; ++w) s += red[(w * 32 + ln) * 16 + q];
+        int dst;
+        if (q < 4) dst = ((q & 2) ? L.vb1 : L.pb1) + ln + ((q & 1) ? 32 : 0);
+        else if (q < 8) dst = (((q - 4) & 2) ? L.vb2 : L.pb2) + ln + (((q - 4) & 1) ? 32 : 0);
+        else if (q < 12) dst = L.aw + ((q - 8) >> 1) * HID + ln + (((q - 8) & 1) ? 32 : 0);
+        else dst = L.cw + ln + ((q - 12) ? 32 : 0);
+        out[dst] = s;
+    }
+    if (tid < 10) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < PG_WARPS; ++w) s += red2[w][tid];
+        const int sb = stat_base(O);
+        if (tid < 2) out[L.ab + tid] = s;
+        else if (tid == 2) out[L.cb] = s;
+        else if (tid < 5) out[L.logstd + tid - 3] = s;   // entropy term added in the reduce kernel
+        else if (tid == 5) { /* unused */ }
+        else out[sb + tid - 6] = s;                      // policy_loss, value_loss, clip_frac, approx_kl sums
+    }
+}
+
+// grad[p] = sum over CTAs (fixed order); finishes the scalar terms.
+__global__ void __launch_bounds__(256)
+ppo_reduce_kernel(const float* __restrict__ partials, int n_parts, int O, float ent_coef,
+                  const double* __restrict__ mb_stats, float* __restrict__ grad, float rank_share) {
+    const int stride = grad_stride(O);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= stride) return;
+    float s = 0.f;
+    for (int b = 0; b < n_parts; ++b) s += partials[(size_t)b * stride + p];
+    const ParamLayout L = make_layout(O);
+    const int sb = stat_base(O);
+    if (p >= L.logstd && p < L.logstd + ACT) s -= ent_coef * rank_share;  // d(-ent_coef * mean entropy)/d log_std
+    if (p >= sb && p < sb + 4) s *= (float)(1.0 / mb_stats[2]);
+    if (p >= sb + 4 || (p >= L.total && p < sb)) s = 0.f;
+    grad[p] = s;
+}
+
+struct AdamArgs {
+    float* params;
+    float* exp_avg;
+    float* exp_avg_sq;
+    const float* grad;
+    int64_t* step;      // device counter, incremented here
+    float lr, beta1, beta2, eps, max_grad_norm;
+    float* info;        // [8]: total_norm, clip_coef, step, 0, then the gradient's stats tail
+    int n_params;       //      (policy_loss, value_loss, clip_fraction, approx_kl)
+};
+
+// clip_grad_norm_ + torch.optim.Adam (single-tensor path, torch 2.0.1 arithmetic order).
+// Single CTA: the 42-48 KB parameter vector is latency-, not bandwidth-bound.
+__global__ void __launch_bounds__(1024) adam_kernel(AdamArgs A) {
+    __shared__ double s_part[32];
+    __shared__ float s_coef;
+    __shared__ double s_bc[2];
+    const int tid = threadIdx.x;
+    double sq = 0.0;
+    for (int p = tid; p < A.n_params; p += blockDim.x) {
+        double g = (double)A.grad[p];
+        sq += g * g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+        float total_norm = (float)sqrt(tot);
+        float coef = A.max_grad_norm / (total_norm + 1e-6f);
+        coef = fminf(coef, 1.0f);
+        s_coef = coef;
+        int64_t step = A.step[0] + 1;
+        A.step[0] = step;
+        s_bc[0] = 1.0 - pow((double)A.beta1, (double)step);
+        s_bc[1] = sqrt(1.0 - pow((double)A.beta2, (double)step));
+        if (A.info) {
+            A.info[0] = total_norm; A.info[1] = coef; A.info[2] = (float)step; A.info[3] = 0.f;
+            const int sb = (A.n_params + 3) & ~3;
+            for (int q = 0; q < 4; ++q) A.info[4 + q] = A.grad[sb + q];
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const float neg_step_size = (float)(-(double)A.lr / s_bc[0]);
+    const float bc2_sqrt = (float)s_bc[1];
+    const float omb1 = 1.f - A.beta1, omb2 = 1.f - A.beta2;
+    for (int p = tid; p < A.n_params; p += blockDim.x) {
+        const float g = __fmul_rn(A.grad[p], coef);
+        const float m = __fadd_rn(__fmul_rn(A.exp_avg[p], A.beta1), __fmul_rn(g, omb1));
+        const float v = __fadd_rn(__fmul_rn(A.exp_avg_sq[p], A.beta2), __fmul_rn(__fmul_rn(g, g), omb2));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), A.eps);
+        A.params[p] = __fadd_rn(A.params[p], __fdiv_rn(__fmul_rn(neg_step_size, m), denom));
+        A.exp_avg[p] = m;
+        A.exp_avg_sq[p] = v;
+    }
+}
+
+// Per-minibatch advantage sums of one epoch's permutation: stats[mb] = (sum, sum of squares,
+// count) in float64 (shifted by the first element to keep the variance well conditioned is not
+// needed at float64).  One CTA per minibatch.
+__global__ void __launch_bounds__(256)
+adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm,
+                 int64_t n_samples, int64_t batch, int64_t N, int64_t T,
+                 double* __restrict__ stats) {
+    const int64_t mb = blockIdx.x;
+    const int64_t s0 = mb * batch, s1 = min(n_samples, s0 + batch);
+    double s = 0.0, q = 0.0;
+    for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+        int64_t id = perm[i];
+        int64_t n = id / T, t = id - n * T;
+        double a = (double)adv[t * N + n];
+        s += a;
+        q += a * a;
+    }
+    __shared__ double sh[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0, tq = 0;
+        for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+        stats[3 * mb] = ts;
+        stats[3 * mb + 1] = tq;
+        stats[3 * mb + 2] = (double)(s1 - s0);
+    }
+}
+
+static size_t grad_smem_bytes(int O, int O_PAD) {
+    size_t f = smem_w_floats(O) + 8192 + (size_t)O_PAD * PG_SP + 3 * 128 * PG_SP + PG_S * 4 +
+               PG_WARPS * 32 * 16;
+    return f * sizeof(float);
+}
+
+}  // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mr_ppo_grad_stride(int obs_dim) { return grad_stride(obs_dim); }
+int mr_ppo_num_params(int obs_dim) { return make_layout(obs_dim).total; }
+int mr_ppo_max_parts(void) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                     int64_t N, int64_t T, double* stats, void* stream) {
+    MR_REQUIRE(adv && perm && stats, "NULL argument");
+    MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
+    int n_mb = ceil_div(n_samples, batch_size);
+    adv_stats_kernel<<<n_mb, 256, 0, (cudaStream_t)stream>>>(adv, perm, n_samples, batch_size, N, T, stats);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
+                const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
+                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
+                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
+                float* partials, float* grad, void* stream) {
+    MR_REQUIRE(params && obs && act && old_logp && adv && ret && perm && mb_stats && partials && grad,
+               "NULL argument");
+    MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
+    MR_REQUIRE(mb_size > 0, "empty minibatch");
+    GradArgs A{params, obs, act, old_logp, adv, ret, perm, mb_size, mb_stats, N, T,
+               clip_range, ent_coef, vf_coef, normalize_adv, partials};
+    const int o_pad = obs_dim <= 16 ? 16 : 32;
+    const size_t smem = grad_smem_bytes(obs_dim, o_pad);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    const int64_t tiles = (mb_size + PG_S - 1) / PG_S;
+    const int grid = (int)std::min<int64_t>(tiles, mr_ppo_max_parts());
+    cudaStream_t s = (cudaStream_t)stream;
+    if (o_pad == 16) ppo_grad_kernel<16><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
+    else ppo_grad_kernel<32><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
+    MR_CHECK_LAUNCH();
+    const int stride = grad_stride(obs_dim);
+    ppo_reduce_kernel<<<ceil_div(stride, 256), 256, 0, s>>>(partials, grid, obs_dim, ent_coef, mb_stats,
+                                                         grad, rank_share);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grad, int n_params,
+                 int64_t* step, float lr, float beta1, float beta2, float eps, float max_grad_norm,
+                 float* info, void* stream) {
+    MR_REQUIRE(params && exp_avg && exp_avg_sq && grad && step, "NULL argument");
+    AdamArgs A{params, exp_avg, exp_avg_sq, grad, step, lr, beta1, beta2, eps, max_grad_norm, info, n_params};
+    adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+"""PPO: the stable-baselines3 ``PPO`` surface mobrob uses, driving the CUDA hot path.
+
+Mirrors (same names, argument meaning, zip format):
+  * ``PPO(env=, seed=, tensorboard_log=, policy="MlpPolicy", n_steps, batch_size, n_epochs,
+    ent_coef, gae_lambda, verbose, device, ...)``       src/mobrob/rl_control/ppo.py:50-59
+  * ``.learn(total_timesteps, callback, progress_bar)``    examples/train.py:42-46
+  * ``.save(path)`` / ``PPO.load(path)``                   ppo.py:76-77, src/mobrob/utils.py:15-16
+  * ``.policy.state_dict() / load_state_dict()``           train.py:30-33
+  * ``.predict(obs, deterministic=True)``                  examples/control.py:39
+One ``learn`` iteration = mr_rollout (T steps) -> mr_gae -> n_epochs x minibatches of
+(mr_ppo_grad [-> all-reduce] -> mr_adam_step).  Nothing here computes on the CPU except
+bookkeeping; there is no fallback path.
+"""
+from __future__ import annotations
+
+import base64
+import io
+import json
+import os
+import sys
+import time
+import zipfile
+from collections import deque
+
+import numpy as np
+import torch
+
+from . import _lib
+from .policy import MlpPolicy
+from .updater import PpoUpdater
+from .vec_env import GpuVecEnv
+
+SB3_VERSION = "2.0.0"
+EP_RING = 1 << 16
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class Logger:
+    """Keeps the reference's log keys; prints SB3-style tables."""
+
+    def __init__(self, verbose=0, tensorboard_log=None):
+        self.name_to_value = {}
+        self.verbose = verbose
+        self.writer = None
+        if tensorboard_log:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+
+                self.writer = SummaryWriter(tensorboard_log)
+            except Exception:
+                self.writer = None
+
+    def record(self, key, value):
+        self.name_to_value[key] = value
+
+    def dump(self, step=0):
+        if self.writer is not None:
+            for k, v in self.name_to_value.items():
+                if isinstance(v, (int, float)):
+                    self.writer.add_scalar(k, v, step)
+        if self.verbose >= 1:
+            groups = {}
+            for k, v in sorted(self.name_to_value.items()):
+                g, _, name = k.partition("/")
+                groups.setdefault(g, []).append((name, v))
+            lines = []
+            for g, items in groups.items():
+                lines.append(f"| {g + '/':<24}|{'':>14} |")
+                for name, v in items:
+                    sv = f"{v:.3g}" if isinstance(v, float) else str(v)
+                    lines.append(f"|    {name:<21}| {sv:<13} |")
+            bar = "-" * 42
+            print("\n".join([bar, *lines, bar]), flush=True)
+        self.name_to_value = {}
+
+
+class PPO:
+    def __init__(self, policy="MlpPolicy", env=None, learning_rate=3e-4, n_steps=2048, batch_size=64,
+                 n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, clip_range_vf=None,
+                 normalize_advantage=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, use_sde=False,
+                 sde_sample_freq=-1, target_kl=None, stats_window_size=100, tensorboard_log=None,
+                 policy_kwargs=None, verbose=0, seed=None, device="auto", _init_setup_model=True,
+                 host_permutation=True):
+        if policy not in ("MlpPolicy", MlpPolicy):
+            raise ValueError("only MlpPolicy is built (the only policy mobrob uses)")
+        if use_sde or clip_range_vf is not None or target_kl is not None:
+            raise NotImplementedError("use_sde / clip_range_vf / target_kl are not used by mobrob's configs")
+        if policy_kwargs not in (None, {}):
+            arch = (policy_kwargs or {}).get("net_arch")
+            if arch not in (None, dict(pi=[64, 64], vf=[64, 64])):
+                raise NotImplementedError("kernels are specialised for net_arch pi=[64,64], vf=[64,64]")
+        if callable(learning_rate):
+            learning_rate = float(learning_rate(1.0))
+        if callable(clip_range):
+            clip_range = float(clip_range(1.0))
+        self.policy_class = MlpPolicy
+        self.policy_kwargs = policy_kwargs or {}
+        self.learning_rate, self.n_steps, self.batch_size, self.n_epochs = learning_rate, n_steps, batch_size, n_epochs
+        self.gamma, self.gae_lambda, self.clip_range = gamma, gae_lambda, clip_range
+        self.normalize_advantage, self.ent_coef, self.vf_coef = normalize_advantage, ent_coef, vf_coef
+        self.max_grad_norm, self.verbose, self.seed = max_grad_norm, verbose, seed
+        self.tensorboard_log = tensorboard_log
+        self.host_permutation = host_permutation  # True: np.random.permutation like SB3 (H2D per epoch)
+        self._stats_window_size = stats_window_size
+        self.num_timesteps = 0
+        self._total_timesteps = 0
+        self._num_timesteps_at_start = 0
+        self._n_updates = 0
+        self._episode_num = 0
+        self.start_time = None
+        self.ep_info_buffer = deque(maxlen=stats_window_size)
+        self.ep_success_buffer = deque(maxlen=stats_window_size)
+        self.env = env
+        self.policy = None
+        self.logger = Logger(verbose, None)
+        self._rollout_count = 0
+        self._ep_seen = 0
+        self._last_obs = None
+        self._last_episode_starts = None
+        self.gpu_time_ms = {}
+        if env is not None:
+            self.n_envs = env.num_envs
+            self.observation_space, self.action_space = env.observation_space, env.action_space
+        if _init_setup_model and env is not None:
+            self._setup_model()
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_model(self):
+        env = self.env
+        if not isinstance(env, GpuVecEnv):
+            raise TypeError("mobrob_b200.PPO trains on a GpuVecEnv (the envs live in HBM)")
+        self.device = env.device
+        if self.seed is not None:  # set_random_seed
+            import random
+
+            random.seed(self.seed)
+            np.random.seed(self.seed)
+            torch.manual_seed(self.seed)
+            env.seed(self.seed)
+        O = env.obs_dim
+        self.updater = PpoUpdater(O, self.device, lr=self.learning_rate, max_grad_norm=self.max_grad_norm,
+                                  clip_range=self.clip_range, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
+                                  normalize_advantage=self.normalize_advantage)
+        self.policy = MlpPolicy(O, 2, device=self.device, flat=self.updater.params, init=True)
+        d = _dist()
+        if d is not None:  # every rank must start from rank 0's parameters
+            d.broadcast(self.updater.params, src=0)
+        T, N = self.n_steps, env.num_envs
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.buf = dict(obs=torch.zeros((T, N, O), **f32), actions=torch.zeros((T, N, 2), **f32),
+                        rewards=torch.zeros((T, N), **f32), episode_starts=torch.zeros((T, N), **f32),
+                        values=torch.zeros((T, N), **f32), log_probs=torch.zeros((T, N), **f32),
+                        advantages=torch.zeros((T, N), **f32), returns=torch.zeros((T, N), **f32))
+        self.last_val = torch.zeros(N, **f32)
+        self.last_done = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self._last_obs = None
+        self._last_episode_starts = None
+        self.ep_r = torch.zeros(EP_RING, dtype=torch.float64, device=self.device)
+        self.ep_l = torch.zeros(EP_RING, dtype=torch.int32, device=self.device)
+        self.ep_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.lib = _lib.load()
+
+    def get_env(self):
+        return self.env
+
+    def set_env(self, env):
+        self.env = env
+        self.n_envs = env.num_envs
+        self._setup_model_buffers_only = True
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # -- rollout ------------------------------------------------------------------------------------
+    def collect_rollouts(self, eps: torch.Tensor | None = None):
+        """Fused rollout of n_steps; eps optionally supplies the N(0,1) draws [T, N, 2]."""
+        env, b = self.env, self.buf
+        if self._last_obs is None:
+            self._last_obs = env.reset_tensor().clone()
+            self._last_episode_starts = torch.ones(env.num_envs, dtype=torch.float32, device=self.device)
+        seed = int(self.seed if self.seed is not None else 0)
+        _lib.check(self.lib.mr_rollout(
+            env._h, self.updater.params.data_ptr(), self.n_steps, self._last_obs.data_ptr(),
+            self._last_episode_starts.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
+            b["rewards"].data_ptr(), b["episode_starts"].data_ptr(), b["values"].data_ptr(),
+            b["log_probs"].data_ptr(), self.last_val.data_ptr(), self.last_done.data_ptr(),
+            None if eps is None else eps.data_ptr(), seed, self._rollout_count * self.n_steps,
+            env.first_rank, float(self.gamma), self.ep_r.data_ptr(), self.ep_l.data_ptr(),
+            self.ep_count.data_ptr(), EP_RING, self._stream()))
+        self._rollout_count += 1
+        _lib.check(self.lib.mr_gae(b["rewards"].data_ptr(), b["values"].data_ptr(),
+                                   b["episode_starts"].data_ptr(), self.last_val.data_ptr(),
+                                   self.last_done.data_ptr(), float(self.gamma), float(self.gae_lambda),
+                                   b["advantages"].data_ptr(), b["returns"].data_ptr(), self.n_steps,
+                                   env.num_envs, self._stream()))
+        self.num_timesteps += self.n_steps * env.num_envs * (self._world_size())
+
+    def _world_size(self):
+        d = _dist()
+        return d.get_world_size() if d is not None else 1
+
+    def _drain_episodes(self):
+        """Monitor's ep_info_buffer: read the finished episodes of the last rollout (one D2H)."""
+        total = int(self.ep_count.item())
+        new = min(total - self._ep_seen, EP_RING)
+        if new > 0:
+            idx = (torch.arange(total - new, total, device=self.device) % EP_RING)
+            r = self.ep_r[idx].cpu().numpy()
+            l = self.ep_l[idx].cpu().numpy()
+            now = round(time.time() - self.env.t_start, 6)
+            for i in range(max(0, new - self._stats_window_size), new):
+                self.ep_info_buffer.append({"r": round(float(r[i]), 6), "l": int(l[i]), "t": now})
+        self._ep_seen = total
+        self._episode_num = total
+
+    # -- update --------------------------------------------------------------------------------------
+    def _permutation(self, n):
+        if self.host_permutation:  # RolloutBuffer.get: np.random.permutation on the global MT19937
+            return torch.as_tensor(np.random.permutation(n).astype(np.int64)).pin_memory().to(
+                self.device, non_blocking=True)
+        return torch.randperm(n, device=self.device, dtype=torch.int64)
+
+    def train(self, perms=None):
+        """PPO.train: n_epochs passes of minibatch updates.  perms: optional list of int64 index
+        arrays (one per epoch) for parity runs; otherwise drawn like RolloutBuffer.get."""
+        up, b = self.updater, self.buf
+        T, N = self.n_steps, self.env.num_envs
+        n = T * N
+        B = self.batch_size
+        n_mb = (n + B - 1) // B
+        d = _dist()
+        log = torch.zeros((self.n_epochs * n_mb, 8), dtype=torch.float32, device=self.device)
+        k = 0
+        for epoch in range(self.n_epochs):
+            perm = perms[epoch] if perms is not None else self._permutation(n)
+            if not torch.is_tensor(perm):
+                perm = torch.as_tensor(np.asarray(perm, dtype=np.int64))
+            perm = perm.to(self.device).contiguous()
+            stats = up.adv_stats(b["advantages"], perm, B, N, T)
+            share = None
+            if d is not None:
+                local_cnt = stats[:, 2].clone()
+                d.all_reduce(stats)
+                share = (local_cnt / stats[:, 2]).cpu().tolist()
+            for mb in range(n_mb):
+                sl = perm[mb * B:(mb + 1) * B]
+                up.compute_grad(b, sl, stats[mb], N, T, 1.0 if share is None else share[mb])
+                if d is not None:
+                    d.all_reduce(up.grad)
+                up.adam_step(log[k])
+                k += 1
+        self._n_updates += self.n_epochs
+        self._train_log = (log[:, 4:], log[:, :4])
+
+    def _log_train(self):
+        tails, log = self._train_log
+        t = tails.mean(dim=0).cpu().numpy()
+        b = self.buf
+        y_pred, y_true = b["values"].flatten(), b["returns"].flatten()
+        var_y = torch.var(y_true)
+        ev = float("nan") if float(var_y) == 0 else float(1 - torch.var(y_true - y_pred) / var_y)
+        ls = self.policy.state_dict()["log_std"]
+        ent = -float((0.5 + 0.5 * np.log(2 * np.pi) + ls).sum())
+        lg = self.logger
+        lg.record("train/entropy_loss", ent)
+        lg.record("train/policy_gradient_loss", float(t[0]))
+        lg.record("train/value_loss", float(t[1]))
+        lg.record("train/approx_kl", float(t[3]))
+        lg.record("train/clip_fraction", float(t[2]))
+        lg.record("train/loss", float(tails[-1, 0] + self.ent_coef * ent + self.vf_coef * tails[-1, 1]))
+        lg.record("train/explained_variance", ev)
+        lg.record("train/std", float(ls.exp().mean()))
+        lg.record("train/n_updates", self._n_updates)
+        lg.record("train/clip_range", self.clip_range)
+        lg.record("train/learning_rate", self.learning_rate)
+
+    # -- learn ----------------------------------------------------------------------------------------
+    def learn(self, total_timesteps, callback=None, log_interval=1, tb_log_name="PPO",
+              reset_num_timesteps=True, progress_bar=False):
+        if reset_num_timesteps or self.start_time is None:
+            self.num_timesteps = 0 if reset_num_timesteps else self.num_timesteps
+            self._num_timesteps_at_start = self.num_timesteps
+            self.start_time = time.time_ns()
+            self._last_obs = None
+            if self.tensorboard_log:
+                self.logger = Logger(self.verbose, os.path.join(self.tensorboard_log, f"{tb_log_name}_1"))
+        self._total_timesteps = total_timesteps + self._num_timesteps_at_start
+        if callback is not None and hasattr(callback, "init_callback"):
+            callback.init_callback(self)
+            callback.on_training_start(locals(), globals())
+        iteration = 0
+        bar = None
+        if progress_bar and self._is_rank0():
+            try:
+                from tqdm import tqdm
+
+                bar = tqdm(total=total_timesteps, file=sys.stderr)
+            except Exception:
+                bar = None
+        while self.num_timesteps < self._total_timesteps:
+            before = self.num_timesteps
+            self.collect_rollouts()
+            if callback is not None and hasattr(callback, "on_rollout_steps"):
+                if callback.on_rollout_steps(self.n_steps) is False:
+                    break
+            iteration += 1
+            if bar is not None:
+                bar.update(self.num_timesteps - before)
+            if log_interval is not None and iteration % log_interval == 0:
+                self._drain_episodes()
+                elapsed = max((time.time_ns() - self.start_time) / 1e9, sys.float_info.epsilon)
+                fps = int((self.num_timesteps - self._num_timesteps_at_start) / elapsed)
+                lg = self.logger
+                if len(self.ep_info_buffer) > 0:
+                    lg.record("rollout/ep_rew_mean", float(np.mean([e["r"] for e in self.ep_info_buffer])))
+                    lg.record("rollout/ep_len_mean", float(np.mean([e["l"] for e in self.ep_info_buffer])))
+                lg.record("time/fps", fps)
+                lg.record("time/iterations", iteration)
+                lg.record("time/time_elapsed", int(elapsed))
+                lg.record("time/total_timesteps", self.num_timesteps)
+                if iteration > 1:
+                    self._log_train()
+                if self._is_rank0():
+                    lg.dump(self.num_timesteps)
+                else:
+                    lg.name_to_value = {}
+            self.train()
+        if bar is not None:
+            bar.close()
+        if callback is not None and hasattr(callback, "on_training_end"):
+            callback.on_training_end()
+        torch.cuda.synchronize(self.device)
+        return self
+
+    @staticmethod
+    def _is_rank0():
+        d = _dist()
+        return d is None or d.get_rank() == 0
+
+    def predict(self, observation, state=None, episode_start=None, deterministic=False):
+        return self.policy.predict(observation, state, episode_start, deterministic)
+
+    # -- zip format ----------------------------------------------------------------
+    def _json_data(self):
+        def ser(obj):
+            try:
+                import cloudpickle
+
+                return base64.b64encode(cloudpickle.dumps(obj)).decode()
+            except Exception:
+                return ""
+
+        def space(sp):
+            return {":type:": "<class 'gymnasium.spaces.box.Box'>", ":serialized:": ser(sp),
+                    "dtype": str(sp.dtype), "bounded_below": str(sp.bounded_below),
+                    "bounded_above": str(sp.bounded_above), "_shape": list(sp.shape),
+                    "low": str(sp.low), "high": str(sp.high), "low_repr": str(sp.low.min()),
+                    "high_repr": str(sp.high.max()), "_np_random": None}
+
+        lr, cr = self.learning_rate, self.clip_range
+        last_obs = None if self._last_obs is None else self._last_obs.cpu().numpy()
+        starts = None if self._last_episode_starts is None else self._last_episode_starts.cpu().numpy().astype(bool)
+        return {
+            "policy_class": {":type:": "<class 'abc.ABCMeta'>", ":serialized:": ser(MlpPolicy),
+                             "__module__": "stable_baselines3.common.policies"},
+            "verbose": self.verbose, "policy_kwargs": {},
+            "num_timesteps": self.num_timesteps, "_total_timesteps": self._total_timesteps,
+            "_num_timesteps_at_start": self._num_timesteps_at_start, "seed": self.seed,
+            "action_noise": None, "start_time": self.start_time, "learning_rate": lr,
+            "tensorboard_log": self.tensorboard_log,
+            "_last_obs": {":type:": "<class 'numpy.ndarray'>", ":serialized:": ser(last_obs)},
+            "_last_episode_starts": {":type:": "<class 'numpy.ndarray'>", ":serialized:": ser(starts)},
+            "_last_original_obs": None, "_episode_num": self._episode_num, "use_sde": False,
+            "sde_sample_freq": -1,
+            "_current_progress_remaining": 1.0 - self.num_timesteps / max(self._total_timesteps, 1),
+            "_stats_window_size": self._stats_window_size,
+            "ep_info_buffer": {":type:": "<class 'collections.deque'>", ":serialized:": ser(self.ep_info_buffer)},
+            "ep_success_buffer": {":type:": "<class 'collections.deque'>", ":serialized:": ser(self.ep_success_buffer)},
+            "_n_updates": self._n_updates, "n_steps": self.n_steps, "gamma": self.gamma,
+            "gae_lambda": self.gae_lambda, "ent_coef": self.ent_coef, "vf_coef": self.vf_coef,
+            "max_grad_norm": self.max_grad_norm, "batch_size": self.batch_size, "n_epochs": self.n_epochs,
+            "clip_range": {":type:": "<class 'function'>", ":serialized:": ser(_Constant(cr)), "value": cr},
+            "clip_range_vf": None, "normalize_advantage": self.normalize_advantage, "target_kl": None,
+            "observation_space": space(self.observation_space), "action_space": space(self.action_space),
+            "n_envs": self.n_envs,
+            "lr_schedule": {":type:": "<class 'function'>", ":serialized:": ser(_Constant(lr)), "value": lr},
+        }
+
+    def save(self, path):
+        path = str(path)
+        if not path.endswith(".zip"):
+            path += ".zip"
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        sd = {k: v.detach().cpu().clone() for k, v in self.policy.state_dict().items()}
+        up = self.updater
+        opt_state, off = {}, 0
+        step = float(up.step.item())
+        for i, (k, v) in enumerate(sd.items()):
+            n = v.numel()
+            opt_state[i] = {"step": torch.tensor(step), "exp_avg": up.exp_avg[off:off + n].view(v.shape).cpu().clone(),
+                            "exp_avg_sq": up.exp_avg_sq[off:off + n].view(v.shape).cpu().clone()}
+            off += n
+        opt = {"state": opt_state if step > 0 else {},
+               "param_groups": [{"lr": up.lr, "betas": tuple(up.betas), "eps": up.eps, "weight_decay": 0,
+                                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                                 "differentiable": False, "fused": None, "params": list(range(len(sd)))}]}
+
+        def pth(obj):
+            bio = io.BytesIO()
+            torch.save(obj, bio)
+            return bio.getvalue()
+
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data", json.dumps(self._json_data(), indent=4))
+            z.writestr("pytorch_variables.pth", pth({}))
+            z.writestr("policy.pth", pth(dict(sd)))
+            z.writestr("policy.optimizer.pth", pth(opt))
+            z.writestr("_stable_baselines3_version", SB3_VERSION)
+            z.writestr("system_info.txt", f"- mobrob_b200 (B200-native)\n- PyTorch: {torch.__version__}\n"
+                                          f"- Numpy: {np.__version__}\n- Stable-Baselines3 format: {SB3_VERSION}\n")
+
+    @classmethod
+    def load(cls, path, env=None, device="auto", custom_objects=None, print_system_info=False,
+             force_reset=True, **kwargs):
+        path = str(path)
+        if not os.path.exists(path) and os.path.exists(path + ".zip"):
+            path += ".zip"
+        with zipfile.ZipFile(path) as z:
+            data = json.loads(z.read("data"))
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+            opt = None
+            if "policy.optimizer.pth" in z.namelist():
+                opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu",
+                                 weights_only=True)
+        plain = ("n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "ent_coef", "vf_coef",
+                 "max_grad_norm", "normalize_advantage", "verbose", "seed")
+        ctor = {k: data[k] for k in plain if k in data}
+        lr = data.get("learning_rate", 3e-4)
+        ctor["learning_rate"] = lr if isinstance(lr, (int, float)) else 3e-4
+        cr = data.get("clip_range", {})
+        ctor["clip_range"] = cr.get("value", 0.2) if isinstance(cr, dict) else float(cr)
+        ctor.update(kwargs)
+        model = cls("MlpPolicy", env, _init_setup_model=False, **ctor)
+        for k in ("num_timesteps", "_total_timesteps", "_num_timesteps_at_start", "_n_updates", "_episode_num"):
+            if k in data:
+                setattr(model, k, data[k])
+        obs_dim = int(data["observation_space"]["_shape"][0])
+        from .spaces import Box
+
+        model.observation_space = Box(-np.inf, np.inf, (obs_dim,), np.float32)
+        model.action_space = Box(-1.0, 1.0, (2,), np.float32)
+        model.n_envs = data.get("n_envs", 1)
+        if env is not None:
+            model._setup_model()
+            up = model.updater
+        else:  # inference-only handle (examples/control.py): policy + optimizer state, no buffers
+            dev = torch.device("cuda", torch.cuda.current_device()) if device == "auto" else torch.device(device)
+            model.device = dev
+            up = PpoUpdater(obs_dim, dev, lr=ctor["learning_rate"], max_grad_norm=ctor.get("max_grad_norm", 0.5),
+                            clip_range=ctor["clip_range"], ent_coef=ctor.get("ent_coef", 0.0),
+                            vf_coef=ctor.get("vf_coef", 0.5),
+                            normalize_advantage=ctor.get("normalize_advantage", True))
+            model.updater = up
+            model.policy = MlpPolicy(obs_dim, 2, device=dev, flat=up.params, init=False)
+        model.policy.load_state_dict(sd)
+        if opt is not None and opt.get("state"):
+            g = opt["param_groups"][0]
+            up.lr, up.betas, up.eps = g["lr"], tuple(g["betas"]), g["eps"]
+            st = opt["state"]
+            up.exp_avg.copy_(torch.cat([st[i]["exp_avg"].reshape(-1) for i in range(len(st))]))
+            up.exp_avg_sq.copy_(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(st))]))
+            up.step.fill_(int(st[0]["step"]))
+        return model
+
+
+class _Constant:
+    """constant_fn(val) of SB3: the schedule objects stored under clip_range / lr_schedule."""
+
+    def __init__(self, val):
+        self.val = float(val)
+
+    def __call__(self, _progress_remaining):
+        return self.val

@@ -1,0 +1,64 @@
+"""Host wrapper around the PPO update kernels (mr_ppo_adv_stats / mr_ppo_grad / mr_adam_step).
+
+Owns the flat parameter vector, the Adam moments and the gradient scratch as torch CUDA
+tensors (so ``state_dict`` views, NCCL all-reduce and checkpointing need no extra copies).
+Mirrors what [SB3] PPO.train does per minibatch; see include/mobrob_b200.h.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class PpoUpdater:
+    def __init__(self, obs_dim: int, device: torch.device, lr: float = 3e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-5, max_grad_norm: float = 0.5, clip_range: float = 0.2,
+                 ent_coef: float = 0.0, vf_coef: float = 0.5, normalize_advantage: bool = True):
+        self.lib = _lib.load()
+        self.obs_dim = obs_dim
+        self.device = device
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.max_grad_norm = max_grad_norm
+        self.clip_range, self.ent_coef, self.vf_coef = clip_range, ent_coef, vf_coef
+        self.normalize_advantage = normalize_advantage
+        self.n_params = int(self.lib.mr_ppo_num_params(obs_dim))
+        self.stride = int(self.lib.mr_ppo_grad_stride(obs_dim))
+        with torch.cuda.device(device):
+            self.max_parts = int(self.lib.mr_ppo_max_parts())
+        f32 = dict(dtype=torch.float32, device=device)
+        self.params = torch.zeros(self.n_params, **f32)
+        self.exp_avg = torch.zeros(self.n_params, **f32)
+        self.exp_avg_sq = torch.zeros(self.n_params, **f32)
+        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.partials = torch.zeros((self.max_parts, self.stride), **f32)
+        self.grad = torch.zeros(self.stride, **f32)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def adv_stats(self, adv: torch.Tensor, perm: torch.Tensor, batch_size: int, N: int, T: int):
+        n = perm.numel()
+        n_mb = (n + batch_size - 1) // batch_size
+        stats = torch.empty((n_mb, 3), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mr_ppo_adv_stats(adv.data_ptr(), perm.data_ptr(), n, batch_size, N, T,
+                                             stats.data_ptr(), self._stream()))
+        return stats
+
+    def compute_grad(self, buf: dict, perm_slice: torch.Tensor, mb_stats: torch.Tensor, N: int, T: int,
+                     rank_share: float = 1.0):
+        """buf: time-major rollout tensors obs/actions/log_probs/advantages/returns."""
+        _lib.check(self.lib.mr_ppo_grad(
+            self.params.data_ptr(), self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(),
+            buf["log_probs"].data_ptr(), buf["advantages"].data_ptr(), buf["returns"].data_ptr(),
+            perm_slice.data_ptr(), perm_slice.numel(), mb_stats.data_ptr(), N, T,
+            self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
+            rank_share, self.partials.data_ptr(), self.grad.data_ptr(), self._stream()))
+        return self.grad
+
+    def adam_step(self, info: torch.Tensor | None = None):
+        _lib.check(self.lib.mr_adam_step(
+            self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            self.grad.data_ptr(), self.n_params, self.step.data_ptr(), self.lr, self.betas[0],
+            self.betas[1], self.eps, self.max_grad_norm, None if info is None else info.data_ptr(),
+            self._stream()))

@@ -1,0 +1,119 @@
+"""CUDA PPO minibatch gradient / Adam step vs torch-CPU autograd (SB3's arithmetic)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sb3_oracle
+
+pytestmark = pytest.mark.gpu
+
+# north_star: PPO losses and gradients within 1e-5 (norm-wise relative)
+RTOL = 1e-5
+
+
+def _make_problem(O, T, N, seed, pretrained_dir=None):
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    old = sb3_oracle.MlpPolicyOracle(O)
+    if pretrained_dir:
+        old.load_numpy(dict(np.load(os.path.join(pretrained_dir, "point_policy.npz"))))
+    else:
+        with torch.no_grad():
+            old.log_std.copy_(torch.tensor([-0.2, 0.3]))
+            old.action_net.weight.mul_(30.0)  # non-trivial means
+    new = copy.deepcopy(old)
+    with torch.no_grad():  # a few updates later: ratio != 1, some samples clipped
+        for p in new.parameters():
+            p.add_(torch.randn_like(p) * (0.02 if pretrained_dir else 0.15) * (p.abs().mean() + 0.01))
+    obs = (torch.randn(T, N, O) * 1.5).numpy().astype(np.float32)
+    eps = torch.randn(T, N, 2)
+    with torch.no_grad():
+        a, v, lp = old.forward_with_noise(torch.as_tensor(obs).reshape(T * N, O), eps.reshape(T * N, 2))
+    buf = dict(obs=obs, actions=a.numpy().reshape(T, N, 2), log_probs=lp.numpy().reshape(T, N),
+               advantages=(rng.standard_normal((T, N)) * 1.3 + 0.2).astype(np.float32),
+               returns=(v.numpy().reshape(T, N) + rng.standard_normal((T, N)).astype(np.float32) * 0.5))
+    return new, buf
+
+
+def _oracle_batch(buf, idx):
+    flat = {k: torch.as_tensor(sb3_oracle.flatten_env_major(buf[k])) for k in buf}
+    b = torch.as_tensor(idx)
+    return (flat["obs"][b], flat["actions"][b], flat["log_probs"][b].flatten(),
+            flat["advantages"][b].flatten(), flat["returns"][b].flatten())
+
+
+def _updater(policy, O, **kw):
+    from mobrob_b200.updater import PpoUpdater
+
+    up = PpoUpdater(O, torch.device("cuda", 0), **kw)
+    up.params.copy_(policy.flat_params())
+    return up
+
+
+@pytest.mark.parametrize("O,T,N,B,pre", [(14, 16, 40, 100, False), (14, 64, 37, 999, True),
+                                        (26, 32, 24, 500, False), (14, 8, 9, 1, False)])
+def test_minibatch_gradient_matches_autograd(cuda_lib, golden_dir, O, T, N, B, pre):
+    pol, buf = _make_problem(O, T, N, seed=O + T, pretrained_dir=golden_dir if pre else None)
+    kw = dict(clip_range=0.2, ent_coef=0.05, vf_coef=0.5, normalize_advantage=True)
+    up = _updater(pol, O, **kw)
+    dbuf = {k: torch.as_tensor(v).cuda().contiguous() for k, v in buf.items()}
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(N * T).astype(np.int64)
+    dperm = torch.as_tensor(perm).cuda()
+    stats = up.adv_stats(dbuf["advantages"], dperm, B, N, T)
+    n_mb = (N * T + B - 1) // B
+    for mb in sorted({0, n_mb // 2, n_mb - 1}):  # includes the short last minibatch
+        idx = perm[mb * B:(mb + 1) * B]
+        loss, st = sb3_oracle.ppo_loss(pol, *_oracle_batch(buf, idx), **kw)
+        pol.zero_grad()
+        loss.backward()
+        g_ref = pol.flat_grads().numpy()
+        g = up.compute_grad(dbuf, dperm[mb * B:(mb + 1) * B], stats[mb], N, T).cpu().numpy()
+        gp, tail = g[:up.n_params], g[up.stride - 16:]
+        err = np.abs(gp - g_ref).max() / np.abs(g_ref).max()
+        assert err < RTOL, f"minibatch {mb}: gradient error {err:.2e}"
+        # per-tensor check too (every tensor has its own scale)
+        off = 0
+        for name in sb3_oracle.PARAM_ORDER:
+            n = dict(pol.named_parameters())[name].numel()
+            ref_t = g_ref[off:off + n]
+            e = np.abs(gp[off:off + n] - ref_t).max() / max(np.abs(ref_t).max(), 1e-3 * np.abs(g_ref).max())
+            assert e < 1e-4, f"{name}: {e:.2e}"
+            off += n
+        np.testing.assert_allclose(tail[0], st["policy_loss"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tail[1], st["value_loss"], rtol=1e-5)
+        np.testing.assert_allclose(tail[2], st["clip_fraction"], atol=1e-6)
+        np.testing.assert_allclose(tail[3], st["approx_kl"], rtol=1e-3, atol=1e-6)
+        if len(idx) > 1:
+            assert st["clip_fraction"] > 0.0  # the problem exercises the clipped branch
+
+
+def test_adam_and_clipping_match_torch(cuda_lib):
+    O, T, N, B = 14, 32, 32, 256
+    pol, buf = _make_problem(O, T, N, seed=3)
+    kw = dict(clip_range=0.2, ent_coef=0.05, vf_coef=0.5, normalize_advantage=True)
+    up = _updater(pol, O, **kw)
+    opt = sb3_oracle.make_adam(pol)
+    dbuf = {k: torch.as_tensor(v).cuda().contiguous() for k, v in buf.items()}
+    rng = np.random.default_rng(2)
+    info = torch.zeros(8, device="cuda")
+    for epoch in range(3):
+        perm = rng.permutation(N * T).astype(np.int64)
+        dperm = torch.as_tensor(perm).cuda()
+        stats = up.adv_stats(dbuf["advantages"], dperm, B, N, T)
+        for mb in range(N * T // B):
+            idx = perm[mb * B:(mb + 1) * B]
+            st, _ = sb3_oracle.train_minibatch(pol, opt, _oracle_batch(buf, idx), max_grad_norm=0.5, **kw)
+            up.compute_grad(dbuf, dperm[mb * B:(mb + 1) * B], stats[mb], N, T)
+            up.adam_step(info)
+            np.testing.assert_allclose(info[0].item(), st["grad_norm"], rtol=1e-4)
+    p_ref = pol.flat_params().numpy()
+    p = up.params.cpu().numpy()
+    # 12 Adam steps of lr 3e-4: parameters move by ~3.6e-3; agreement is relative to that motion
+    assert int(up.step.item()) == 12
+    assert np.abs(p - p_ref).max() < 2e-6
+    m_ref = torch.cat([opt.state[q]["exp_avg"].reshape(-1) for q in opt.param_groups[0]["params"]]).numpy()
+    np.testing.assert_allclose(up.exp_avg.cpu().numpy(), m_ref, rtol=1e-3, atol=1e-7)
