@@ -137,6 +137,14 @@ int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float*
                 float ent_coef, float vf_coef, int normalize_adv, float rank_share,
                 float* partials, float* grad, void* stream);
 
+/* The forward/backward kernel of mr_ppo_grad alone: per-CTA partial gradients, no reduction
+ * (*n_parts rows of `partials` are valid).  Exposed so bench.py can time the dominant kernel. */
+int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, const float* act,
+                         const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
+                         int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
+                         float ent_coef, float vf_coef, int normalize_adv, float* partials, int* n_parts,
+                         void* stream);
+
 /* clip_grad_norm_(max_grad_norm) then torch.optim.Adam.step (eps as given; SB3 uses 1e-5).
  * step: device int64 counter (state["step"]), incremented.  info [8] out (may be NULL):
  * total grad norm, clip coefficient, step, 0, then grad's stats tail (policy_loss, value_loss,
@@ -163,6 +171,16 @@ int mr_rollout(mr_env* env, const float* params, int64_t T, float* last_obs, flo
                float* last_val, uint8_t* last_done, const float* eps, uint64_t seed,
                uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
                int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
+
+/* One epoch of PPO.train on one GPU: for every minibatch of perm, mr_ppo_grad then mr_adam_step,
+ * launched back to back from C (no host round trip between minibatches).  stats [n_mb][3] from
+ * mr_ppo_adv_stats; info [n_mb][8] receives mr_adam_step's info rows (may be NULL). */
+int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
+                       const float* obs, const float* act, const float* old_logp, const float* adv,
+                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                       const double* stats, int64_t N, int64_t T, float clip_range, float ent_coef,
+                       float vf_coef, int normalize_adv, float lr, float beta1, float beta2, float eps,
+                       float max_grad_norm, float* partials, float* grad, float* info, void* stream);
 
 #ifdef __cplusplus
 }

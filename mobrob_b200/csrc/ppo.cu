@@ -556,12 +556,12 @@ int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, i
     return MR_OK;
 }
 
-int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
-                const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
-                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
-                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
-                float* partials, float* grad, void* stream) {
-    MR_REQUIRE(params && obs && act && old_logp && adv && ret && perm && mb_stats && partials && grad,
+int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, const float* act,
+                         const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
+                         int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
+                         float ent_coef, float vf_coef, int normalize_adv, float* partials, int* n_parts,
+                         void* stream) {
+    MR_REQUIRE(params && obs && act && old_logp && adv && ret && perm && mb_stats && partials,
                "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     MR_REQUIRE(mb_size > 0, "empty minibatch");
@@ -575,15 +575,31 @@ int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float*
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
+    static int max_parts = 0;
+    if (!max_parts) max_parts = mr_ppo_max_parts();
     const int64_t tiles = (mb_size + PG_S - 1) / PG_S;
-    const int grid = (int)std::min<int64_t>(tiles, mr_ppo_max_parts());
+    const int grid = (int)std::min<int64_t>(tiles, max_parts);
     cudaStream_t s = (cudaStream_t)stream;
     if (o_pad == 16) ppo_grad_kernel<16><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
     else ppo_grad_kernel<32><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
     MR_CHECK_LAUNCH();
+    if (n_parts) *n_parts = grid;
+    return MR_OK;
+}
+
+int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
+                const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
+                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
+                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
+                float* partials, float* grad, void* stream) {
+    MR_REQUIRE(grad, "NULL argument");
+    int grid = 0;
+    int rc = mr_ppo_grad_partials(params, obs_dim, obs, act, old_logp, adv, ret, perm, mb_size, mb_stats,
+                                  N, T, clip_range, ent_coef, vf_coef, normalize_adv, partials, &grid, stream);
+    if (rc != MR_OK) return rc;
     const int stride = grad_stride(obs_dim);
-    ppo_reduce_kernel<<<ceil_div(stride, 256), 256, 0, s>>>(partials, grid, obs_dim, ent_coef, mb_stats,
-                                                         grad, rank_share);
+    ppo_reduce_kernel<<<ceil_div(stride, 256), 256, 0, (cudaStream_t)stream>>>(
+        partials, grid, obs_dim, ent_coef, mb_stats, grad, rank_share);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -595,6 +611,28 @@ int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* 
     AdamArgs A{params, exp_avg, exp_avg_sq, grad, step, lr, beta1, beta2, eps, max_grad_norm, info, n_params};
     adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A);
     MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
+                       const float* obs, const float* act, const float* old_logp, const float* adv,
+                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                       const double* stats, int64_t N, int64_t T, float clip_range, float ent_coef,
+                       float vf_coef, int normalize_adv, float lr, float beta1, float beta2, float eps,
+                       float max_grad_norm, float* partials, float* grad, float* info, void* stream) {
+    MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
+    const int n_params = make_layout(obs_dim).total;
+    const int64_t n_mb = (n_samples + batch_size - 1) / batch_size;
+    for (int64_t mb = 0; mb < n_mb; ++mb) {
+        const int64_t s0 = mb * batch_size;
+        const int64_t sz = std::min(batch_size, n_samples - s0);
+        int rc = mr_ppo_grad(params, obs_dim, obs, act, old_logp, adv, ret, perm + s0, sz, stats + 3 * mb,
+                             N, T, clip_range, ent_coef, vf_coef, normalize_adv, 1.0f, partials, grad, stream);
+        if (rc != MR_OK) return rc;
+        rc = mr_adam_step(params, exp_avg, exp_avg_sq, grad, n_params, step, lr, beta1, beta2, eps,
+                          max_grad_norm, info ? info + 8 * mb : nullptr, stream);
+        if (rc != MR_OK) return rc;
+    }
     return MR_OK;
 }
 

@@ -244,16 +244,17 @@ class PPO:
                 perm = torch.as_tensor(np.asarray(perm, dtype=np.int64))
             perm = perm.to(self.device).contiguous()
             stats = up.adv_stats(b["advantages"], perm, B, N, T)
-            share = None
-            if d is not None:
-                local_cnt = stats[:, 2].clone()
-                d.all_reduce(stats)
-                share = (local_cnt / stats[:, 2]).cpu().tolist()
+            if d is None:
+                up.train_epoch(b, perm, stats, B, N, T, log[k:k + n_mb])
+                k += n_mb
+                continue
+            local_cnt = stats[:, 2].clone()
+            d.all_reduce(stats)
+            share = (local_cnt / stats[:, 2]).cpu().tolist()
             for mb in range(n_mb):
                 sl = perm[mb * B:(mb + 1) * B]
-                up.compute_grad(b, sl, stats[mb], N, T, 1.0 if share is None else share[mb])
-                if d is not None:
-                    d.all_reduce(up.grad)
+                up.compute_grad(b, sl, stats[mb], N, T, share[mb])
+                d.all_reduce(up.grad)
                 up.adam_step(log[k])
                 k += 1
         self._n_updates += self.n_epochs

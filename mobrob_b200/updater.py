@@ -56,9 +56,29 @@ class PpoUpdater:
             rank_share, self.partials.data_ptr(), self.grad.data_ptr(), self._stream()))
         return self.grad
 
+    def compute_partials(self, buf: dict, perm_slice: torch.Tensor, mb_stats: torch.Tensor, N: int, T: int):
+        """Forward/backward kernel only (per-CTA partial gradients) -- used for kernel timing."""
+        _lib.check(self.lib.mr_ppo_grad_partials(
+            self.params.data_ptr(), self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(),
+            buf["log_probs"].data_ptr(), buf["advantages"].data_ptr(), buf["returns"].data_ptr(),
+            perm_slice.data_ptr(), perm_slice.numel(), mb_stats.data_ptr(), N, T,
+            self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
+            self.partials.data_ptr(), None, self._stream()))
+
     def adam_step(self, info: torch.Tensor | None = None):
         _lib.check(self.lib.mr_adam_step(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
             self.grad.data_ptr(), self.n_params, self.step.data_ptr(), self.lr, self.betas[0],
             self.betas[1], self.eps, self.max_grad_norm, None if info is None else info.data_ptr(),
             self._stream()))
+
+    def train_epoch(self, buf: dict, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int, T: int,
+                    info: torch.Tensor | None = None):
+        """All minibatches of one epoch, launched from C (single-GPU path)."""
+        _lib.check(self.lib.mr_ppo_train_epoch(
+            self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
+            self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
+            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(), perm.numel(), batch_size,
+            stats.data_ptr(), N, T, self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
+            self.lr, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, self.partials.data_ptr(),
+            self.grad.data_ptr(), None if info is None else info.data_ptr(), self._stream()))
