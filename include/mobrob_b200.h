@@ -146,7 +146,8 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
                          void* stream);
 
 /* clip_grad_norm_(max_grad_norm) then torch.optim.Adam.step (eps as given; SB3 uses 1e-5).
- * step: device int64 counter (state["step"]), incremented.  info [8] out (may be NULL):
+ * step: device int64[2]: [0] = Adam step count (state["step"]), incremented; [1] = launch-internal
+ * ticket that must start at 0.  info [8] out (may be NULL):
  * total grad norm, clip coefficient, step, 0, then grad's stats tail (policy_loss, value_loss,
  * clip_fraction, approx_kl) so that logging needs no extra copy. */
 int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grad, int n_params,

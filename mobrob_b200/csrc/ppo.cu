@@ -414,15 +414,27 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int
     }
 }
 
-// grad[p] = sum over CTAs (fixed order); finishes the scalar terms.
-__global__ void __launch_bounds__(256)
+// grad[p] = sum over CTAs; finishes the scalar terms.  One thread per parameter; the n_parts
+// loads are independent, so they are issued 8 deep into 4 interleaved accumulators that are
+// combined in a fixed order (deterministic for a given n_parts).
+__global__ void __launch_bounds__(128)
 ppo_reduce_kernel(const float* __restrict__ partials, int n_parts, int O, float ent_coef,
                   const double* __restrict__ mb_stats, float* __restrict__ grad, float rank_share) {
     const int stride = grad_stride(O);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= stride) return;
-    float s = 0.f;
-    for (int b = 0; b < n_parts; ++b) s += partials[(size_t)b * stride + p];
+    const float* src = partials + p;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 8 <= n_parts; b += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (size_t)(b + q) * stride);
+        a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+        a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+    }
+    for (; b < n_parts; ++b) a0 += __ldg(src + (size_t)b * stride);
+    float s = (a0 + a1) + (a2 + a3);
     const ParamLayout L = make_layout(O);
     const int sb = stat_base(O);
     if (p >= L.logstd && p < L.logstd + ACT) s -= ent_coef * rank_share;  // d(-ent_coef * mean entropy)/d log_std
@@ -436,51 +448,58 @@ struct AdamArgs {
     float* exp_avg;
     float* exp_avg_sq;
     const float* grad;
-    int64_t* step;      // device counter, incremented here
+    int64_t* step;      // [0] Adam step count (state["step"]); [1] launch-internal ticket (starts at 0)
     float lr, beta1, beta2, eps, max_grad_norm;
     float* info;        // [8]: total_norm, clip_coef, step, 0, then the gradient's stats tail
     int n_params;       //      (policy_loss, value_loss, clip_fraction, approx_kl)
 };
 
+constexpr int ADAM_THREADS = 256;
+
 // clip_grad_norm_ + torch.optim.Adam (single-tensor path, torch 2.0.1 arithmetic order).
-// Single CTA: the 42-48 KB parameter vector is latency-, not bandwidth-bound.
-__global__ void __launch_bounds__(1024) adam_kernel(AdamArgs A) {
-    __shared__ double s_part[32];
-    __shared__ float s_coef;
+// The vector is only 42-48 KB, so the kernel is latency-bound: one parameter per thread,
+// every CTA recomputes the global norm from L2 in the same fixed order (bit-identical across
+// CTAs, no inter-CTA barrier), and the last CTA to finish bumps the step counter.
+__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(AdamArgs A) {
+    __shared__ double s_part[ADAM_THREADS / 32];
     __shared__ double s_bc[2];
     const int tid = threadIdx.x;
+    const int64_t step = A.step[0] + 1;
+    if (tid == 0) {
+        s_bc[0] = 1.0 - pow((double)A.beta1, (double)step);
+        s_bc[1] = sqrt(1.0 - pow((double)A.beta2, (double)step));
+    }
+    // global grad norm: thread t sums elements t, t + 256, ... (independent loads)
     double sq = 0.0;
-    for (int p = tid; p < A.n_params; p += blockDim.x) {
-        double g = (double)A.grad[p];
-        sq += g * g;
+    {
+        constexpr int U = 8;
+        int p = tid;
+        for (; p + (U - 1) * ADAM_THREADS < A.n_params; p += U * ADAM_THREADS) {
+            float v[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) v[q] = __ldg(A.grad + p + q * ADAM_THREADS);
+#pragma unroll
+            for (int q = 0; q < U; ++q) sq += (double)v[q] * (double)v[q];
+        }
+        for (; p < A.n_params; p += ADAM_THREADS) {
+            float v = __ldg(A.grad + p);
+            sq += (double)v * (double)v;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if ((tid & 31) == 0) s_part[tid >> 5] = sq;
     __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
-        float total_norm = (float)sqrt(tot);
-        float coef = A.max_grad_norm / (total_norm + 1e-6f);
-        coef = fminf(coef, 1.0f);
-        s_coef = coef;
-        int64_t step = A.step[0] + 1;
-        A.step[0] = step;
-        s_bc[0] = 1.0 - pow((double)A.beta1, (double)step);
-        s_bc[1] = sqrt(1.0 - pow((double)A.beta2, (double)step));
-        if (A.info) {
-            A.info[0] = total_norm; A.info[1] = coef; A.info[2] = (float)step; A.info[3] = 0.f;
-            const int sb = (A.n_params + 3) & ~3;
-            for (int q = 0; q < 4; ++q) A.info[4 + q] = A.grad[sb + q];
-        }
-    }
-    __syncthreads();
-    const float coef = s_coef;
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < ADAM_THREADS / 32; ++w) tot += s_part[w];
+    const float total_norm = (float)sqrt(tot);
+    const float coef = fminf(A.max_grad_norm / (total_norm + 1e-6f), 1.0f);
     const float neg_step_size = (float)(-(double)A.lr / s_bc[0]);
     const float bc2_sqrt = (float)s_bc[1];
     const float omb1 = 1.f - A.beta1, omb2 = 1.f - A.beta2;
-    for (int p = tid; p < A.n_params; p += blockDim.x) {
+    const int p = blockIdx.x * ADAM_THREADS + tid;
+    if (p < A.n_params) {
         const float g = __fmul_rn(A.grad[p], coef);
         const float m = __fadd_rn(__fmul_rn(A.exp_avg[p], A.beta1), __fmul_rn(g, omb1));
         const float v = __fadd_rn(__fmul_rn(A.exp_avg_sq[p], A.beta2), __fmul_rn(__fmul_rn(g, g), omb2));
@@ -488,6 +507,21 @@ __global__ void __launch_bounds__(1024) adam_kernel(AdamArgs A) {
         A.params[p] = __fadd_rn(A.params[p], __fdiv_rn(__fmul_rn(neg_step_size, m), denom));
         A.exp_avg[p] = m;
         A.exp_avg_sq[p] = v;
+    }
+    if (blockIdx.x == 0 && tid == 0 && A.info) {
+        A.info[0] = total_norm; A.info[1] = coef; A.info[2] = (float)step; A.info[3] = 0.f;
+        const int sb = (A.n_params + 3) & ~3;
+        for (int q = 0; q < 4; ++q) A.info[4 + q] = A.grad[sb + q];
+    }
+    // last CTA out increments the step (every CTA has read it by then) and re-arms the ticket
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned long long* ticket = reinterpret_cast<unsigned long long*>(A.step + 1);
+        if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1) {
+            A.step[0] = step;
+            *ticket = 0ull;
+        }
     }
 }
 
@@ -598,7 +632,7 @@ int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float*
                                   N, T, clip_range, ent_coef, vf_coef, normalize_adv, partials, &grid, stream);
     if (rc != MR_OK) return rc;
     const int stride = grad_stride(obs_dim);
-    ppo_reduce_kernel<<<ceil_div(stride, 256), 256, 0, (cudaStream_t)stream>>>(
+    ppo_reduce_kernel<<<ceil_div(stride, 128), 128, 0, (cudaStream_t)stream>>>(
         partials, grid, obs_dim, ent_coef, mb_stats, grad, rank_share);
     MR_CHECK_LAUNCH();
     return MR_OK;
@@ -609,7 +643,7 @@ int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* 
                  float* info, void* stream) {
     MR_REQUIRE(params && exp_avg && exp_avg_sq && grad && step, "NULL argument");
     AdamArgs A{params, exp_avg, exp_avg_sq, grad, step, lr, beta1, beta2, eps, max_grad_norm, info, n_params};
-    adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A);
+    adam_kernel<<<ceil_div(n_params, ADAM_THREADS), ADAM_THREADS, 0, (cudaStream_t)stream>>>(A);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }

@@ -402,7 +402,7 @@ class PPO:
         sd = {k: v.detach().cpu().clone() for k, v in self.policy.state_dict().items()}
         up = self.updater
         opt_state, off = {}, 0
-        step = float(up.step.item())
+        step = float(up.step[0].item())
         for i, (k, v) in enumerate(sd.items()):
             n = v.numel()
             opt_state[i] = {"step": torch.tensor(step), "exp_avg": up.exp_avg[off:off + n].view(v.shape).cpu().clone(),
@@ -477,7 +477,7 @@ class PPO:
             st = opt["state"]
             up.exp_avg.copy_(torch.cat([st[i]["exp_avg"].reshape(-1) for i in range(len(st))]))
             up.exp_avg_sq.copy_(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(st))]))
-            up.step.fill_(int(st[0]["step"]))
+            up.step[0] = int(st[0]["step"])
         return model
 
 

@@ -30,7 +30,7 @@ class PpoUpdater:
         self.params = torch.zeros(self.n_params, **f32)
         self.exp_avg = torch.zeros(self.n_params, **f32)
         self.exp_avg_sq = torch.zeros(self.n_params, **f32)
-        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.step = torch.zeros(2, dtype=torch.int64, device=device)  # [count, kernel ticket]
         self.partials = torch.zeros((self.max_parts, self.stride), **f32)
         self.grad = torch.zeros(self.stride, **f32)
 

@@ -113,7 +113,7 @@ def test_adam_and_clipping_match_torch(cuda_lib):
     p_ref = pol.flat_params().numpy()
     p = up.params.cpu().numpy()
     # 12 Adam steps of lr 3e-4: parameters move by ~3.6e-3; agreement is relative to that motion
-    assert int(up.step.item()) == 12
+    assert int(up.step[0].item()) == 12
     assert np.abs(p - p_ref).max() < 2e-6
     m_ref = torch.cat([opt.state[q]["exp_avg"].reshape(-1) for q in opt.param_groups[0]["params"]]).numpy()
     np.testing.assert_allclose(up.exp_avg.cpu().numpy(), m_ref, rtol=1e-3, atol=1e-7)

@@ -160,7 +160,7 @@ def test_save_load_roundtrip_and_reference_zip(cuda_lib, golden_dir, tmp_path):
 
     ref = PPO.load(os.path.join(golden_dir, "policies", "point-ppo.zip"))
     assert ref.n_steps == 4000 and ref.batch_size == 100 and ref.gae_lambda == 0.5 and ref.ent_coef == 0.05
-    assert int(ref.updater.step.item()) == 100000 and ref.updater.eps == 1e-5
+    assert int(ref.updater.step[0].item()) == 100000 and ref.updater.eps == 1e-5
     obs = np.load(os.path.join(golden_dir, "point_last_obs.npy"))
     a, _ = ref.predict(obs[0], deterministic=True)
     assert a.shape == (2,) and a.dtype == np.float32
