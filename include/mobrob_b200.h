@@ -183,6 +183,27 @@ int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t
                        float vf_coef, int normalize_adv, float lr, float beta1, float beta2, float eps,
                        float max_grad_norm, float* partials, float* grad, float* info, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fused epoch: every minibatch of one epoch of PPO.train in ONE cooperative launch (forward,
+ * backward, gradient reduction, [all-reduce,] clip_grad_norm_, Adam; grid barriers in between).
+ * With xchg != NULL the per-minibatch gradient all-reduce (the reference has none: SB3 trains in
+ * one process) runs inside the kernel over NVLink peer memory: each CTA pushes its slice of the
+ * gradient into every peer's inbox, raises a flag, and sums the ranks' slices in rank order.
+ * rank_share [n_mb] device floats (local / global minibatch count) or NULL. */
+typedef struct mr_xchg mr_xchg;
+/* Allocate this rank's inbox; h_handle_out receives its 64-byte CUDA IPC handle. */
+int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out);
+/* h_all_handles [world][64]: every rank's handle (gathered by the host, e.g. torch.distributed). */
+int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles);
+void mr_xchg_destroy(mr_xchg* x);
+int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
+                       const float* obs, const float* act, const float* old_logp, const float* adv,
+                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                       const double* stats, const float* rank_share, int64_t N, int64_t T,
+                       float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
+                       float beta1, float beta2, float eps, float max_grad_norm, float* partials,
+                       float* grad, float* info, mr_xchg* xchg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

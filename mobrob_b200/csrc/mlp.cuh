@@ -54,7 +54,8 @@ struct SmemW {
 
 __host__ __device__ inline int smem_w_floats(int O) { return 128 * O + 8192 + 128 + 128 + 192 + 4 + 4; }
 
-// All threads of the block cooperate; caller must __syncthreads() afterwards.
+// All threads of the block cooperate; caller must __syncthreads() afterwards.  Loads go through
+// L2 (ld.cg): the persistent epoch kernel re-stages parameters another CTA has just updated.
 __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ params, int O) {
     const ParamLayout L = make_layout(O);
     float* w1 = smem;
@@ -68,26 +69,26 @@ __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ par
         int k = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
         int u = lane + ((j & 1) ? 32 : 0);
         int base = (j & 2) ? L.vw1 : L.pw1;
-        w1[idx] = params[base + u * O + k];
+        w1[idx] = __ldcg(params + base + u * O + k);
     }
     for (int idx = threadIdx.x; idx < 8192; idx += blockDim.x) {
         int k = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
         int u = lane + ((j & 1) ? 32 : 0);
         int base = (j & 2) ? L.vw2 : L.pw2;
-        w2[idx] = params[base + u * HID + k];
+        w2[idx] = __ldcg(params + base + u * HID + k);
     }
     for (int idx = threadIdx.x; idx < 128; idx += blockDim.x) {
         int lane = idx >> 2, j = idx & 3;
         int u = lane + ((j & 1) ? 32 : 0);
-        b1[idx] = params[((j & 2) ? L.vb1 : L.pb1) + u];
-        b2[idx] = params[((j & 2) ? L.vb2 : L.pb2) + u];
+        b1[idx] = __ldcg(params + ((j & 2) ? L.vb1 : L.pb1) + u);
+        b2[idx] = __ldcg(params + ((j & 2) ? L.vb2 : L.pb2) + u);
     }
     for (int idx = threadIdx.x; idx < 192; idx += blockDim.x)
-        hw[idx] = idx < 128 ? params[L.aw + idx] : params[L.cw + idx - 128];
+        hw[idx] = idx < 128 ? __ldcg(params + L.aw + idx) : __ldcg(params + L.cw + idx - 128);
     if (threadIdx.x < 4) {
-        hb[threadIdx.x] = threadIdx.x < 2 ? params[L.ab + threadIdx.x]
-                                          : (threadIdx.x == 2 ? params[L.cb] : 0.f);
-        ls[threadIdx.x] = threadIdx.x < 2 ? params[L.logstd + threadIdx.x] : 0.f;
+        hb[threadIdx.x] = threadIdx.x < 2 ? __ldcg(params + L.ab + threadIdx.x)
+                                          : (threadIdx.x == 2 ? __ldcg(params + L.cb) : 0.f);
+        ls[threadIdx.x] = threadIdx.x < 2 ? __ldcg(params + L.logstd + threadIdx.x) : 0.f;
     }
     SmemW W;
     W.w1p = reinterpret_cast<const float4*>(w1);

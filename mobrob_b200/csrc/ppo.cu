@@ -14,6 +14,8 @@
 //     order (deterministic), adam_kernel clips by global norm and applies torch's Adam.
 #include "mlp.cuh"
 
+#include <string.h>
+
 namespace mr {
 
 constexpr int PG_WARPS = 8;
@@ -43,29 +45,49 @@ struct GradArgs {
     float* partials;        // [gridDim.x][grad_stride]
 };
 
-template <int O_PAD>
-__global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int O) {
-    extern __shared__ __align__(16) float smem[];
-    const ParamLayout L = make_layout(O);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+struct GradSmem {
+    SmemW W;
+    float4* w2b;  // [u][lane] backward pack of W2
+    float *X, *H1, *H2, *Z1, *dOut, *red;
+};
 
-    // ---- shared memory carve-up ---------------------------------------------------------
+// Carve the dynamic shared memory and (re)stage the parameters: all threads of the CTA cooperate;
+// the caller must __syncthreads() before using them.
+template <int O_PAD>
+__device__ __forceinline__ GradSmem grad_stage(float* smem, const float* __restrict__ params, int O,
+                                               bool first) {
+    const ParamLayout L = make_layout(O);
+    const int tid = threadIdx.x;
+    GradSmem S;
     float* p = smem;
-    SmemW W = stage_weights(p, A.params, O);        p += smem_w_floats(O);
-    float4* w2b = reinterpret_cast<float4*>(p);     p += 8192;   // [u][lane] backward pack
-    float* X = p;                                   p += O_PAD * PG_SP;
-    float* H1 = p;                                  p += 128 * PG_SP;
-    float* H2 = p;                                  p += 128 * PG_SP;   // becomes dZ2
-    float* Z1 = p;                                  p += 128 * PG_SP;   // dZ1
-    float* dOut = p;                                p += PG_S * 4;
-    float* red = p;                                 /* PG_WARPS * 32 * 16 floats */
+    S.W = stage_weights(p, params, O);              p += smem_w_floats(O);
+    S.w2b = reinterpret_cast<float4*>(p);           p += 8192;
+    S.X = p;                                        p += O_PAD * PG_SP;
+    S.H1 = p;                                       p += 128 * PG_SP;
+    S.H2 = p;                                       p += 128 * PG_SP;   // becomes dZ2
+    S.Z1 = p;                                       p += 128 * PG_SP;   // dZ1
+    S.dOut = p;                                     p += PG_S * 4;
+    S.red = p;                                      /* PG_WARPS * 32 * 16 floats */
     for (int idx = tid; idx < 8192; idx += PG_THREADS) {
         int u = idx >> 7, r = idx & 127, ln = r >> 2, j = r & 3;
         int k = ln + ((j & 1) ? 32 : 0);
-        reinterpret_cast<float*>(w2b)[idx] = A.params[((j & 2) ? L.vw2 : L.pw2) + u * HID + k];
+        reinterpret_cast<float*>(S.w2b)[idx] = __ldcg(params + ((j & 2) ? L.vw2 : L.pw2) + u * HID + k);
     }
-    for (int idx = tid; idx < O_PAD * PG_SP; idx += PG_THREADS) X[idx] = 0.f;
-    __syncthreads();
+    if (first)
+        for (int idx = tid; idx < O_PAD * PG_SP; idx += PG_THREADS) S.X[idx] = 0.f;
+    return S;
+}
+
+// One minibatch on this CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; writes the CTA's
+// partial gradient (all grad_stride(O) - STAT_SLOTS + 4 used entries) to `out`.
+template <int O_PAD>
+__device__ __forceinline__ void grad_minibatch(const GradArgs& A, int O, const GradSmem& S,
+                                               float* __restrict__ out) {
+    const ParamLayout L = make_layout(O);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const SmemW& W = S.W;
+    const float4* w2b = S.w2b;
+    float *X = S.X, *H1 = S.H1, *H2 = S.H2, *Z1 = S.Z1, *dOut = S.dOut, *red = S.red;
 
     // ---- minibatch constants ----------------------------------------------------------------
     const double cnt = A.mb_stats[2];
@@ -353,7 +375,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int
     }
 
     // ---- write this CTA's partial gradient ------------------------------------------------------
-    float* out = A.partials + (size_t)blockIdx.x * grad_stride(O);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -412,6 +433,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int
         else if (tid == 5) { /* unused */ }
         else out[sb + tid - 6] = s;                      // policy_loss, value_loss, clip_frac, approx_kl sums
     }
+}
+
+template <int O_PAD>
+__global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int O) {
+    extern __shared__ __align__(16) float smem[];
+    GradSmem S = grad_stage<O_PAD>(smem, A.params, O, true);
+    __syncthreads();
+    grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)blockIdx.x * grad_stride(O));
 }
 
 // grad[p] = sum over CTAs; finishes the scalar terms.  One thread per parameter; the n_parts
@@ -559,6 +588,199 @@ adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent epoch kernel: every minibatch of one epoch in ONE cooperative launch (one CTA per SM).
+// Per minibatch: [stage parameters] -> forward/backward (grad_minibatch) -> grid barrier ->
+// each CTA reduces its slice of the gradient over all CTAs' partials [-> one-shot all-reduce over
+// NVLink peer memory: push the slice into every peer's inbox, flag, sum in rank order] -> slice
+// sum of squares -> grid barrier -> global-norm clip + Adam on the slice -> grid barrier.
+// Replaces 3 launches (+ an NCCL call) per minibatch; everything is summed in a fixed order, so
+// parameters stay bit-identical across ranks.
+struct PeerXchg {
+    int world, rank;
+    float* inbox;              // local  [2][world][stride]
+    unsigned* inflag;          // local  [world][n_cta]
+    float* peer_inbox[8];      // peers' inboxes (NVLink-mapped)
+    unsigned* peer_inflag[8];
+};
+
+struct EpochArgs {
+    GradArgs G;
+    int64_t n_samples, batch;
+    const double* stats;       // [n_mb][3] (global minibatch sums)
+    const float* rank_share;   // [n_mb] local count / global count, NULL -> 1
+    float *params, *exp_avg, *exp_avg_sq;
+    int64_t* step;
+    float lr, beta1, beta2, eps, max_grad_norm;
+    float* grad;               // [stride] last reduced gradient
+    float* info;               // [n_mb][8] or NULL
+    double* sq;                // [n_cta] scratch
+    unsigned* barrier;         // [1], zero at launch
+    unsigned seq0;             // exchange sequence number before this launch
+    PeerXchg X;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned n_cta) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += n_cta;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_gpu(counter) < target) {}
+    }
+    __syncthreads();
+}
+
+constexpr int EP_MAX_SLICE = 128;
+
+template <int O_PAD>
+__global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, int O) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_grp[PG_THREADS];
+    __shared__ double s_dred[PG_WARPS];
+    __shared__ double s_scal[4];
+    const ParamLayout L = make_layout(O);
+    const int tid = threadIdx.x;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int stride = grad_stride(O), sb = stat_base(O), n_params = L.total;
+    const int slice = (((stride + G - 1) / G) + 3) & ~3;
+    const int groups = PG_THREADS / slice;            // part-groups summing in parallel
+    const int p0 = c * slice;
+    const int64_t n_mb = (E.n_samples + E.batch - 1) / E.batch;
+    unsigned target = 0;
+    int64_t step = E.step[0];
+    const float omb1 = 1.f - E.beta1, omb2 = 1.f - E.beta2;
+
+    for (int64_t m = 0; m < n_mb; ++m) {
+        GradSmem S = grad_stage<O_PAD>(smem, E.params, O, m == 0);
+        __syncthreads();
+        GradArgs A = E.G;
+        A.params = E.params;
+        A.perm = E.G.perm + m * E.batch;
+        A.mb_size = min(E.batch, E.n_samples - m * E.batch);
+        A.mb_stats = E.stats + 3 * m;
+        grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)c * stride);
+        grid_barrier(E.barrier, target, G);
+
+        // ---- phase B: this CTA's slice of the gradient --------------------------------------------
+        ++step;
+        if (tid == PG_THREADS - 1) {  // bias corrections, off the critical path
+            s_scal[0] = 1.0 - pow((double)E.beta1, (double)step);
+            s_scal[1] = sqrt(1.0 - pow((double)E.beta2, (double)step));
+        }
+        const int j = tid % slice, g = tid / slice;
+        const int p = p0 + j;
+        float part = 0.f;
+        if (g < groups && p < stride) {
+            const float* src = A.partials + p;
+            float a0 = 0.f, a1 = 0.f;
+            int b = g;
+            for (; b + 7 * groups < G; b += 8 * groups) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(b + q * groups) * stride);
+                a0 += v[0]; a1 += v[1]; a0 += v[2]; a1 += v[3];
+                a0 += v[4]; a1 += v[5]; a0 += v[6]; a1 += v[7];
+            }
+            for (; b < G; b += groups) a0 += __ldcg(src + (size_t)b * stride);
+            part = a0 + a1;
+        }
+        s_grp[tid] = part;
+        __syncthreads();
+        float val = 0.f;
+        const bool own = tid < slice && p < stride;
+        if (own) {
+            for (int q = 0; q < groups; ++q) val += s_grp[q * slice + j];
+            const float share = E.rank_share ? E.rank_share[m] : 1.f;
+            if (p >= L.logstd && p < L.logstd + ACT) val -= E.G.ent_coef * share;
+            if (p >= sb && p < sb + 4) val *= (float)(1.0 / A.mb_stats[2]);
+            if (p >= sb + 4 || (p >= n_params && p < sb)) val = 0.f;
+        }
+        if (E.X.world > 1) {  // one-shot all-reduce over NVLink peer memory (push, flag, sum in rank order)
+            const unsigned seq = E.seq0 + (unsigned)m + 1u;
+            const int slot = seq & 1u;
+            if (own) {
+                for (int r = 0; r < E.X.world; ++r)
+                    if (r != E.X.rank)
+                        E.X.peer_inbox[r][((size_t)slot * E.X.world + E.X.rank) * stride + p] = val;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < E.X.world && tid != E.X.rank) {
+                st_release_sys(E.X.peer_inflag[tid] + (size_t)E.X.rank * G + c, seq);
+                while (ld_acquire_sys(E.X.inflag + (size_t)tid * G + c) < seq) {}
+            }
+            __syncthreads();
+            if (own) {
+                float tot = 0.f;
+                for (int r = 0; r < E.X.world; ++r)
+                    tot += (r == E.X.rank) ? val
+                                           : __ldcv(E.X.inbox + ((size_t)slot * E.X.world + r) * stride + p);
+                val = tot;
+            }
+        }
+        double sq = 0.0;
+        if (own) {
+            E.grad[p] = val;
+            if (p < n_params) sq = (double)val * (double)val;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if ((tid & 31) == 0) s_dred[tid >> 5] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < PG_WARPS; ++w) t += s_dred[w];
+            E.sq[c] = t;
+        }
+        grid_barrier(E.barrier, target, G);
+
+        // ---- phase C: global-norm clip + Adam on the slice ----------------------------------------------
+        if (tid < 32) {
+            double t = 0.0;
+            for (int b = tid; b < G; b += 32) t += __ldcg(E.sq + b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (tid == 0) s_scal[2] = t;
+        }
+        __syncthreads();
+        const float total_norm = (float)sqrt(s_scal[2]);
+        const float coef = fminf(E.max_grad_norm / (total_norm + 1e-6f), 1.0f);
+        const float neg_step_size = (float)(-(double)E.lr / s_scal[0]);
+        const float bc2_sqrt = (float)s_scal[1];
+        if (own && p < n_params) {
+            const float gq = __fmul_rn(val, coef);
+            const float mq = __fadd_rn(__fmul_rn(E.exp_avg[p], E.beta1), __fmul_rn(gq, omb1));
+            const float vq = __fadd_rn(__fmul_rn(E.exp_avg_sq[p], E.beta2), __fmul_rn(__fmul_rn(gq, gq), omb2));
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vq), bc2_sqrt), E.eps);
+            E.params[p] = __fadd_rn(E.params[p], __fdiv_rn(__fmul_rn(neg_step_size, mq), denom));
+            E.exp_avg[p] = mq;
+            E.exp_avg_sq[p] = vq;
+        }
+        if (E.info) {
+            float* row = E.info + 8 * m;
+            if (c == 0 && tid == 0) { row[0] = total_norm; row[1] = coef; row[2] = (float)step; row[3] = 0.f; }
+            if (own && p >= sb && p < sb + 4) row[4 + p - sb] = val;
+        }
+        grid_barrier(E.barrier, target, G);
+    }
+    if (c == 0 && tid == 0) E.step[0] = step;
+}
+
 static size_t grad_smem_bytes(int O, int O_PAD) {
     size_t f = smem_w_floats(O) + 8192 + (size_t)O_PAD * PG_SP + 3 * 128 * PG_SP + PG_S * 4 +
                PG_WARPS * 32 * 16;
@@ -667,6 +889,122 @@ int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t
                           max_grad_norm, info ? info + 8 * mb : nullptr, stream);
         if (rc != MR_OK) return rc;
     }
+    return MR_OK;
+}
+
+struct mr_xchg {
+    int world, rank, device, n_cta;
+    int64_t stride;
+    void* base;            // local allocation: inbox floats then flags
+    size_t bytes;
+    void* peer_base[8];
+    unsigned seq;          // exchange sequence number (host mirror)
+};
+
+static size_t xchg_inbox_bytes(int world, int64_t stride) { return (size_t)2 * world * stride * sizeof(float); }
+
+int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out) {
+    MR_REQUIRE(out && h_handle_out, "NULL argument");
+    MR_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad world/rank");
+    MR_CUDA(cudaSetDevice(device));
+    mr_xchg* x = new mr_xchg();
+    x->world = world; x->rank = rank; x->device = device;
+    x->n_cta = mr_ppo_max_parts();
+    x->stride = grad_stride(obs_dim);
+    x->bytes = xchg_inbox_bytes(world, x->stride) + (size_t)world * x->n_cta * sizeof(unsigned);
+    x->seq = 0;
+    for (int r = 0; r < 8; ++r) x->peer_base[r] = nullptr;
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); delete x; return MR_ERR_ALLOC; }
+    MR_CUDA(cudaMemset(x->base, 0, x->bytes));
+    cudaIpcMemHandle_t h;
+    MR_CUDA(cudaIpcGetMemHandle(&h, x->base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(h_handle_out, &h, 64);
+    x->peer_base[rank] = x->base;
+    *out = x;
+    return MR_OK;
+}
+
+int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles) {
+    MR_REQUIRE(x && h_all_handles, "NULL argument");
+    MR_CUDA(cudaSetDevice(x->device));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_all_handles + 64 * r, 64);
+        MR_CUDA(cudaIpcOpenMemHandle(&x->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return MR_OK;
+}
+
+void mr_xchg_destroy(mr_xchg* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    cudaFree(x->base);
+    delete x;
+}
+
+int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
+                       const float* obs, const float* act, const float* old_logp, const float* adv,
+                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
+                       const double* stats, const float* rank_share, int64_t N, int64_t T,
+                       float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
+                       float beta1, float beta2, float eps, float max_grad_norm, float* partials,
+                       float* grad, float* info, mr_xchg* xchg, void* stream) {
+    MR_REQUIRE(params && exp_avg && exp_avg_sq && step && obs && act && old_logp && adv && ret && perm &&
+                   stats && partials && grad, "NULL argument");
+    MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
+    MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0;
+    MR_CUDA(cudaGetDevice(&dev));
+    static void* scratch[16] = {nullptr};
+    MR_REQUIRE(dev < 16, "device index out of range");
+    if (!scratch[dev]) MR_CUDA(cudaMalloc(&scratch[dev], 4096));
+    const int n_cta = mr_ppo_max_parts();
+    MR_REQUIRE(n_cta <= 448, "too many SMs for the scratch layout");
+    EpochArgs E;
+    E.G = GradArgs{params, obs, act, old_logp, adv, ret, perm, 0, stats, N, T,
+                   clip_range, ent_coef, vf_coef, normalize_adv, partials};
+    E.n_samples = n_samples; E.batch = batch_size; E.stats = stats; E.rank_share = rank_share;
+    E.params = params; E.exp_avg = exp_avg; E.exp_avg_sq = exp_avg_sq; E.step = step;
+    E.lr = lr; E.beta1 = beta1; E.beta2 = beta2; E.eps = eps; E.max_grad_norm = max_grad_norm;
+    E.grad = grad; E.info = info;
+    E.sq = reinterpret_cast<double*>(scratch[dev]);
+    E.barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch[dev]) + 3840);
+    MR_CUDA(cudaMemsetAsync(E.barrier, 0, sizeof(unsigned), s));
+    E.X.world = 1; E.X.rank = 0; E.X.inbox = nullptr; E.X.inflag = nullptr;
+    E.seq0 = 0;
+    const int64_t n_mb = (n_samples + batch_size - 1) / batch_size;
+    if (xchg && xchg->world > 1) {
+        MR_REQUIRE(xchg->stride == grad_stride(obs_dim) && xchg->n_cta == n_cta, "exchange buffer mismatch");
+        E.X.world = xchg->world; E.X.rank = xchg->rank;
+        const size_t off = xchg_inbox_bytes(xchg->world, xchg->stride);
+        for (int r = 0; r < xchg->world; ++r) {
+            E.X.peer_inbox[r] = reinterpret_cast<float*>(xchg->peer_base[r]);
+            E.X.peer_inflag[r] = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xchg->peer_base[r]) + off);
+        }
+        E.X.inbox = E.X.peer_inbox[xchg->rank];
+        E.X.inflag = E.X.peer_inflag[xchg->rank];
+        E.seq0 = xchg->seq;
+        xchg->seq += (unsigned)n_mb;
+    }
+    const int o_pad = obs_dim <= 16 ? 16 : 32;
+    const size_t smem = grad_smem_bytes(obs_dim, o_pad);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    int O = obs_dim;
+    void* args[] = {&E, &O};
+    const void* fn = o_pad == 16 ? (const void*)ppo_epoch_kernel<16> : (const void*)ppo_epoch_kernel<32>;
+    MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(PG_THREADS), args, smem, s));
+    mr::count_launch();
     return MR_OK;
 }
 

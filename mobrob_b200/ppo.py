@@ -25,7 +25,7 @@ from collections import deque
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from .policy import MlpPolicy
 from .updater import PpoUpdater
 from .vec_env import GpuVecEnv
@@ -87,7 +87,7 @@ class PPO:
                  normalize_advantage=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, use_sde=False,
                  sde_sample_freq=-1, target_kl=None, stats_window_size=100, tensorboard_log=None,
                  policy_kwargs=None, verbose=0, seed=None, device="auto", _init_setup_model=True,
-                 host_permutation=True):
+                 host_permutation=True, update_mode="fused"):
         if policy not in ("MlpPolicy", MlpPolicy):
             raise ValueError("only MlpPolicy is built (the only policy mobrob uses)")
         if use_sde or clip_range_vf is not None or target_kl is not None:
@@ -124,6 +124,8 @@ class PPO:
         self._ep_seen = 0
         self._last_obs = None
         self._last_episode_starts = None
+        self._xchg = None
+        self.update_mode = update_mode  # "fused" | "launches" (per-minibatch kernels, NCCL when sharded)
         self.gpu_time_ms = {}
         if env is not None:
             self.n_envs = env.num_envs
@@ -244,19 +246,28 @@ class PPO:
                 perm = torch.as_tensor(np.asarray(perm, dtype=np.int64))
             perm = perm.to(self.device).contiguous()
             stats = up.adv_stats(b["advantages"], perm, B, N, T)
-            if d is None:
+            share = None
+            if d is not None:
+                stats, share = sharding.allreduce_adv_stats(stats)
+                share = share.to(torch.float32).contiguous()
+            if self.update_mode == "fused":      # one cooperative launch per epoch (+ NVLink all-reduce)
+                if d is not None and self._xchg is None:
+                    from .updater import PeerExchange
+
+                    self._xchg = PeerExchange(up.obs_dim, self.device)
+                up.train_epoch_fused(b, perm, stats, B, N, T, log[k:k + n_mb], share, self._xchg)
+                k += n_mb
+            elif d is None:                      # 3 launches per minibatch, looped in C
                 up.train_epoch(b, perm, stats, B, N, T, log[k:k + n_mb])
                 k += n_mb
-                continue
-            local_cnt = stats[:, 2].clone()
-            d.all_reduce(stats)
-            share = (local_cnt / stats[:, 2]).cpu().tolist()
-            for mb in range(n_mb):
-                sl = perm[mb * B:(mb + 1) * B]
-                up.compute_grad(b, sl, stats[mb], N, T, share[mb])
-                d.all_reduce(up.grad)
-                up.adam_step(log[k])
-                k += 1
+            else:                                # NCCL all-reduce per minibatch (baseline path)
+                share_h = share.cpu().tolist()
+                for mb in range(n_mb):
+                    sl = perm[mb * B:(mb + 1) * B]
+                    up.compute_grad(b, sl, stats[mb], N, T, share_h[mb])
+                    d.all_reduce(up.grad)
+                    up.adam_step(log[k])
+                    k += 1
         self._n_updates += self.n_epochs
         self._train_log = (log[:, 4:], log[:, :4])
 

@@ -82,3 +82,45 @@ class PpoUpdater:
             stats.data_ptr(), N, T, self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
             self.lr, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, self.partials.data_ptr(),
             self.grad.data_ptr(), None if info is None else info.data_ptr(), self._stream()))
+
+    def train_epoch_fused(self, buf: dict, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int,
+                          T: int, info: torch.Tensor | None = None, rank_share: torch.Tensor | None = None,
+                          xchg=None):
+        """One cooperative launch for the whole epoch; xchg (PeerExchange) adds the in-kernel
+        NVLink all-reduce of the gradient."""
+        _lib.check(self.lib.mr_ppo_epoch_fused(
+            self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
+            self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
+            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(), perm.numel(), batch_size,
+            stats.data_ptr(), None if rank_share is None else rank_share.data_ptr(), N, T, self.clip_range,
+            self.ent_coef, self.vf_coef, int(self.normalize_advantage), self.lr, self.betas[0], self.betas[1],
+            self.eps, self.max_grad_norm, self.partials.data_ptr(), self.grad.data_ptr(),
+            None if info is None else info.data_ptr(), None if xchg is None else xchg.handle, self._stream()))
+
+
+class PeerExchange:
+    """Per-rank inbox in CUDA-IPC-shared device memory for the in-kernel gradient all-reduce."""
+
+    def __init__(self, obs_dim: int, device: torch.device):
+        import ctypes
+
+        import numpy as np
+        import torch.distributed as dist
+
+        self.lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        h = ctypes.c_void_p()
+        mine = np.zeros(64, dtype=np.uint8)
+        _lib.check(self.lib.mr_xchg_create(self.world, self.rank, device.index or 0, obs_dim, ctypes.byref(h),
+                                           mine.ctypes.data))
+        self.handle = h
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine.tobytes())
+        flat = np.frombuffer(b"".join(allh), dtype=np.uint8).copy()
+        _lib.check(self.lib.mr_xchg_connect(self.handle, flat.ctypes.data))
+        dist.barrier()
+
+    def close(self):
+        if getattr(self, "handle", None) is not None:
+            self.lib.mr_xchg_destroy(self.handle)
+            self.handle = None

@@ -117,3 +117,27 @@ def test_adam_and_clipping_match_torch(cuda_lib):
     assert np.abs(p - p_ref).max() < 2e-6
     m_ref = torch.cat([opt.state[q]["exp_avg"].reshape(-1) for q in opt.param_groups[0]["params"]]).numpy()
     np.testing.assert_allclose(up.exp_avg.cpu().numpy(), m_ref, rtol=1e-3, atol=1e-7)
+
+
+def test_fused_epoch_kernel_matches_per_minibatch_launches(cuda_lib):
+    """The persistent cooperative epoch kernel == grad / reduce / Adam launched per minibatch."""
+    O, T, N, B = 14, 64, 48, 700   # 4.4 minibatches: last one short; fewer tiles than CTAs
+    pol, buf = _make_problem(O, T, N, seed=5)
+    kw = dict(clip_range=0.2, ent_coef=0.05, vf_coef=0.5, normalize_advantage=True)
+    a, b = _updater(pol, O, **kw), _updater(pol, O, **kw)
+    dbuf = {k: torch.as_tensor(v).cuda().contiguous() for k, v in buf.items()}
+    rng = np.random.default_rng(4)
+    n_mb = (N * T + B - 1) // B
+    ia, ib = torch.zeros((n_mb, 8), device="cuda"), torch.zeros((n_mb, 8), device="cuda")
+    p0 = a.params.clone()
+    for epoch in range(3):
+        dperm = torch.as_tensor(rng.permutation(N * T).astype(np.int64)).cuda()
+        stats = a.adv_stats(dbuf["advantages"], dperm, B, N, T)
+        a.train_epoch(dbuf, dperm, stats, B, N, T, ia)
+        b.train_epoch_fused(dbuf, dperm, stats, B, N, T, ib)
+    torch.cuda.synchronize()
+    moved = float((a.params - p0).abs().max())
+    assert moved > 1e-3
+    assert float((a.params - b.params).abs().max()) < 1e-4 * moved
+    assert int(a.step[0]) == int(b.step[0]) == 3 * n_mb
+    np.testing.assert_allclose(ib.cpu().numpy(), ia.cpu().numpy(), rtol=2e-4, atol=1e-6)

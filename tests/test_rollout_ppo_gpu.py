@@ -177,3 +177,24 @@ def test_save_load_roundtrip_and_reference_zip(cuda_lib, golden_dir, tmp_path):
     names = set(zipfile.ZipFile(out).namelist())
     assert {"data", "policy.pth", "policy.optimizer.pth", "pytorch_variables.pth",
             "_stable_baselines3_version", "system_info.txt"} <= names
+
+
+def test_pretrained_point_policy_reaches_goals(cuda_lib, golden_dir):
+    """BASELINE configs[1] in small: deterministic shipped policy, goal reached within the 1000-step
+    limit; CUDA vs oracle on the same seeds (success rate within 1 %, as north_star asks)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import eval_policy
+
+    z = os.path.join(golden_dir, "policies", "point-ppo.zip")
+    n = 96
+    g = eval_policy.evaluate_gpu(z, n, steps=400)
+    o = eval_policy.evaluate_oracle(z, n, steps=400)
+    assert abs(g["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.0105
+    assert o["first_goal_success_rate"] > 0.9
+    # un-saturated deterministic actions are sensitive (DESIGN.md "Sensitivity"): lengths may differ by a step or two
+    assert np.abs(g["first_len"] - o["first_len"]).max() <= 4
+    assert (g["first_len"] == o["first_len"]).mean() > 0.6
+    big = eval_policy.evaluate_gpu(z, 4096, steps=400)
+    assert abs(big["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.03
