@@ -56,11 +56,10 @@ struct GradSmem {
 template <int O_PAD>
 __device__ __forceinline__ GradSmem grad_stage(float* smem, const float* __restrict__ params, int O,
                                                bool first) {
-    const ParamLayout L = make_layout(O);
     const int tid = threadIdx.x;
     GradSmem S;
     float* p = smem;
-    S.W = stage_weights(p, params, O);              p += smem_w_floats(O);
+    float* wf = p;                                  p += smem_w_floats(O);
     S.w2b = reinterpret_cast<float4*>(p);           p += 8192;
     S.X = p;                                        p += O_PAD * PG_SP;
     S.H1 = p;                                       p += 128 * PG_SP;
@@ -68,11 +67,11 @@ __device__ __forceinline__ GradSmem grad_stage(float* smem, const float* __restr
     S.Z1 = p;                                       p += 128 * PG_SP;   // dZ1
     S.dOut = p;                                     p += PG_S * 4;
     S.red = p;                                      /* PG_WARPS * 32 * 16 floats */
-    for (int idx = tid; idx < 8192; idx += PG_THREADS) {
-        int u = idx >> 7, r = idx & 127, ln = r >> 2, j = r & 3;
-        int k = ln + ((j & 1) ? 32 : 0);
-        reinterpret_cast<float*>(S.w2b)[idx] = __ldcg(params + ((j & 2) ? L.vw2 : L.pw2) + u * HID + k);
-    }
+    // the activation buffers are idle here: use them for the raw parameter image
+    static_assert(2 * 128 * PG_SP >= 2 * HID * (MAX_OBS + 1) + 2 * HID * (HID + 1) + 1024, "raw image fits");
+    stage_raw(S.H1, params, O);
+    __syncthreads();
+    S.W = pack_from_raw(wf, reinterpret_cast<float*>(S.w2b), S.H1, O);
     if (first)
         for (int idx = tid; idx < O_PAD * PG_SP; idx += PG_THREADS) S.X[idx] = 0.f;
     return S;
@@ -592,16 +591,15 @@ adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm
 // Persistent epoch kernel: every minibatch of one epoch in ONE cooperative launch (one CTA per SM).
 // Per minibatch: [stage parameters] -> forward/backward (grad_minibatch) -> grid barrier ->
 // each CTA reduces its slice of the gradient over all CTAs' partials [-> one-shot all-reduce over
-// NVLink peer memory: push the slice into every peer's inbox, flag, sum in rank order] -> slice
+// NVLink peer memory: push the slice into every peer's inbox as tagged 8-byte packets, spin on the
+// tags, sum in rank order] -> slice
 // sum of squares -> grid barrier -> global-norm clip + Adam on the slice -> grid barrier.
 // Replaces 3 launches (+ an NCCL call) per minibatch; everything is summed in a fixed order, so
 // parameters stay bit-identical across ranks.
 struct PeerXchg {
     int world, rank;
-    float* inbox;              // local  [2][world][stride]
-    unsigned* inflag;          // local  [world][n_cta]
-    float* peer_inbox[8];      // peers' inboxes (NVLink-mapped)
-    unsigned* peer_inflag[8];
+    unsigned long long* inbox;          // local  [2][world][stride] packets {seq << 32 | float bits}
+    unsigned long long* peer_inbox[8];  // peers' inboxes (NVLink-mapped)
 };
 
 struct EpochArgs {
@@ -644,8 +642,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     }
     __syncthreads();
 }
-
-constexpr int EP_MAX_SLICE = 128;
 
 template <int O_PAD>
 __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, int O) {
@@ -710,26 +706,30 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
             if (p >= sb && p < sb + 4) val *= (float)(1.0 / A.mb_stats[2]);
             if (p >= sb + 4 || (p >= n_params && p < sb)) val = 0.f;
         }
-        if (E.X.world > 1) {  // one-shot all-reduce over NVLink peer memory (push, flag, sum in rank order)
+        if (E.X.world > 1) {
+            // One-shot all-reduce over NVLink peer memory, low-latency protocol: every element
+            // travels as one 8-byte store {value, sequence tag}; the receiver spins on the tag of
+            // the element itself, so there is no fence, no flag and no second round trip.
+            // Two parity slots: slot (seq & 1) is rewritten at seq + 2, which a rank can only
+            // reach after every peer has pushed seq + 1, i.e. after it consumed seq.
             const unsigned seq = E.seq0 + (unsigned)m + 1u;
             const int slot = seq & 1u;
             if (own) {
+                const unsigned long long pkt =
+                    ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(val);
                 for (int r = 0; r < E.X.world; ++r)
                     if (r != E.X.rank)
-                        E.X.peer_inbox[r][((size_t)slot * E.X.world + E.X.rank) * stride + p] = val;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < E.X.world && tid != E.X.rank) {
-                st_release_sys(E.X.peer_inflag[tid] + (size_t)E.X.rank * G + c, seq);
-                while (ld_acquire_sys(E.X.inflag + (size_t)tid * G + c) < seq) {}
-            }
-            __syncthreads();
-            if (own) {
+                        __stcg(E.X.peer_inbox[r] + ((size_t)slot * E.X.world + E.X.rank) * stride + p, pkt);
                 float tot = 0.f;
-                for (int r = 0; r < E.X.world; ++r)
-                    tot += (r == E.X.rank) ? val
-                                           : __ldcv(E.X.inbox + ((size_t)slot * E.X.world + r) * stride + p);
+                for (int r = 0; r < E.X.world; ++r) {  // rank order: bit-identical on every rank
+                    if (r == E.X.rank) { tot += val; continue; }
+                    const unsigned long long* src = E.X.inbox + ((size_t)slot * E.X.world + r) * stride + p;
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                    } while ((unsigned)(v >> 32) != seq);
+                    tot += __uint_as_float((unsigned)v);
+                }
                 val = tot;
             }
         }
@@ -901,7 +901,9 @@ struct mr_xchg {
     unsigned seq;          // exchange sequence number (host mirror)
 };
 
-static size_t xchg_inbox_bytes(int world, int64_t stride) { return (size_t)2 * world * stride * sizeof(float); }
+static size_t xchg_inbox_bytes(int world, int64_t stride) {
+    return (size_t)2 * world * stride * sizeof(unsigned long long);
+}
 
 int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out) {
     MR_REQUIRE(out && h_handle_out, "NULL argument");
@@ -911,7 +913,7 @@ int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, 
     x->world = world; x->rank = rank; x->device = device;
     x->n_cta = mr_ppo_max_parts();
     x->stride = grad_stride(obs_dim);
-    x->bytes = xchg_inbox_bytes(world, x->stride) + (size_t)world * x->n_cta * sizeof(unsigned);
+    x->bytes = xchg_inbox_bytes(world, x->stride);
     x->seq = 0;
     for (int r = 0; r < 8; ++r) x->peer_base[r] = nullptr;
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
@@ -976,19 +978,15 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     E.sq = reinterpret_cast<double*>(scratch[dev]);
     E.barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch[dev]) + 3840);
     MR_CUDA(cudaMemsetAsync(E.barrier, 0, sizeof(unsigned), s));
-    E.X.world = 1; E.X.rank = 0; E.X.inbox = nullptr; E.X.inflag = nullptr;
+    E.X.world = 1; E.X.rank = 0; E.X.inbox = nullptr;
     E.seq0 = 0;
     const int64_t n_mb = (n_samples + batch_size - 1) / batch_size;
     if (xchg && xchg->world > 1) {
         MR_REQUIRE(xchg->stride == grad_stride(obs_dim) && xchg->n_cta == n_cta, "exchange buffer mismatch");
         E.X.world = xchg->world; E.X.rank = xchg->rank;
-        const size_t off = xchg_inbox_bytes(xchg->world, xchg->stride);
-        for (int r = 0; r < xchg->world; ++r) {
-            E.X.peer_inbox[r] = reinterpret_cast<float*>(xchg->peer_base[r]);
-            E.X.peer_inflag[r] = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xchg->peer_base[r]) + off);
-        }
+        for (int r = 0; r < xchg->world; ++r)
+            E.X.peer_inbox[r] = reinterpret_cast<unsigned long long*>(xchg->peer_base[r]);
         E.X.inbox = E.X.peer_inbox[xchg->rank];
-        E.X.inflag = E.X.peer_inflag[xchg->rank];
         E.seq0 = xchg->seq;
         xchg->seq += (unsigned)n_mb;
     }
