@@ -56,6 +56,10 @@ void mr_env_destroy(mr_env* env);
 int mr_env_obs_dim(const mr_env* env);   /* point 14, car 26 (engine.py:420-567) */
 int mr_env_state_dim(const mr_env* env); /* doubles per env in get/set_state */
 
+/* Test hook (car): 0 disables the floor contacts, giving the contact-free trajectories on which
+ * BASELINE.json asks for 1e-5 state parity.  Default 1. */
+int mr_env_set_contacts(mr_env* env, int enabled);
+
 /* EnvWrapper.seed (wrapper.py:95-107) for every env: the two gymnasium Box streams
  * (init_space -> PCG64(SeedSequence(s)), goal_space -> PCG64(SeedSequence(s + 1))) arrive as
  * raw PCG64 words [N][4] = (state_hi, state_lo, inc_hi, inc_lo); engine_seed [N] is
@@ -83,7 +87,8 @@ int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* 
 /* EnvWrapper.get_obs (wrapper.py:272-273 -> Engine.obs, engine.py:1174-1263). */
 int mr_env_get_obs(mr_env* env, float* obs_out, void* stream);
 /* Reference-view state, [N][state_dim] float64.
- * point: qpos(3) qvel(3) body_pos_xy(2) start_heading(1) ctrl(2) goal_xy(2) elapsed(1) ep_ret(1) */
+ * point (15): qpos(3) qvel(3) body_pos_xy(2) start_heading(1) ctrl(2) goal_xy(2) elapsed(1) ep_ret(1)
+ * car (30):   qpos(13) qvel(11) ctrl(2) goal_xy(2) elapsed(1) ep_ret(1), MuJoCo joint order */
 int mr_env_get_state(mr_env* env, double* state_out, void* stream);
 int mr_env_set_state(mr_env* env, const double* state_in, void* stream);
 /* EnvWrapper.get_pos (wrapper.py:269-270): world xy, [N][2] float64. */

@@ -148,6 +148,167 @@ __global__ void point_get_pos_kernel(PointState st, double* __restrict__ out) {
     out[2 * i + 1] = st.py[i];
 }
 
+// ---------------------------------------------------------------------------------------
+// car: same VecEnv kernels, one thread per env (state in local fp64, ~0.4 MFLOP per env-step)
+constexpr int CAR_THREADS = 64;
+
+__global__ void __launch_bounds__(CAR_THREADS)
+car_step_kernel(CarSoA st, car::Consts K, EnvCfg cfg, const float2* __restrict__ act,
+                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                uint8_t* __restrict__ trunc, float* __restrict__ term_obs, double* __restrict__ ep_ret,
+                int32_t* __restrict__ ep_len) {
+    const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    CarHot h = st.load(i);
+    float2 a = act[i];
+    float o[car::OBS], tobs[car::OBS];
+    StepResult r = car_env_step(K, h, st.cold, i, a.x, a.y, cfg, st.contacts != 0, o, tobs);
+    st.store(i, h);
+    for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+    rew[i] = r.rew;
+    done[i] = r.done ? 1 : 0;
+    trunc[i] = r.trunc ? 1 : 0;
+    if (r.done) {
+        if (term_obs) for (int k = 0; k < car::OBS; ++k) term_obs[i * car::OBS + k] = tobs[k];
+        if (ep_ret) ep_ret[i] = r.ep_r;
+        if (ep_len) ep_len[i] = r.ep_l;
+    }
+}
+
+__global__ void __launch_bounds__(CAR_THREADS)
+car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int first, float* __restrict__ obs) {
+    const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    if (mask && !mask[i]) return;
+    CarHot h = st.load(i);
+    bool reach = point::dist2((double)h.gx, (double)h.gy, h.s.p[0], h.s.p[1]) < REACH_RADIUS;
+    car_reset(h, st.cold, i, first || !reach);
+    st.store(i, h);
+    if (obs) {
+        float o[car::OBS];
+        car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o);
+        for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+    }
+}
+
+__global__ void __launch_bounds__(CAR_THREADS)
+car_obs_kernel(CarSoA st, car::Consts K, float* __restrict__ obs) {
+    const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    CarHot h = st.load(i);
+    float o[car::OBS];
+    car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o);
+    for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+}
+
+// reference view: qpos(13) = p quat thL thR qb ; qvel(11) = v w sL sR wb ; ctrl goal elapsed ep_ret
+__global__ void car_get_state_kernel(CarSoA st, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    CarHot h = st.load(i);
+    double* o = out + i * CAR_STATE_DIM;
+    const car::State& s = h.s;
+    o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
+    o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
+    o[7] = s.th[0]; o[8] = s.th[1];
+    o[9] = s.qb[0]; o[10] = s.qb[1]; o[11] = s.qb[2]; o[12] = s.qb[3];
+    o[13] = s.v[0]; o[14] = s.v[1]; o[15] = s.v[2];
+    o[16] = s.w[0]; o[17] = s.w[1]; o[18] = s.w[2];
+    o[19] = s.s[0]; o[20] = s.s[1];
+    o[21] = s.wb[0]; o[22] = s.wb[1]; o[23] = s.wb[2];
+    o[24] = h.cx; o[25] = h.cz; o[26] = h.gx; o[27] = h.gy;
+    o[28] = (double)h.elapsed; o[29] = h.ep_ret;
+}
+
+__global__ void car_set_state_kernel(CarSoA st, const double* __restrict__ in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    const double* o = in + i * CAR_STATE_DIM;
+    CarHot h;
+    car::State& s = h.s;
+    s.p[0] = o[0]; s.p[1] = o[1]; s.p[2] = o[2];
+    s.q[0] = o[3]; s.q[1] = o[4]; s.q[2] = o[5]; s.q[3] = o[6];
+    s.th[0] = o[7]; s.th[1] = o[8];
+    s.qb[0] = o[9]; s.qb[1] = o[10]; s.qb[2] = o[11]; s.qb[3] = o[12];
+    s.v[0] = o[13]; s.v[1] = o[14]; s.v[2] = o[15];
+    s.w[0] = o[16]; s.w[1] = o[17]; s.w[2] = o[18];
+    s.s[0] = o[19]; s.s[1] = o[20];
+    s.wb[0] = o[21]; s.wb[1] = o[22]; s.wb[2] = o[23];
+    h.cx = (float)o[24]; h.cz = (float)o[25]; h.gx = (float)o[26]; h.gy = (float)o[27];
+    h.elapsed = (int)o[28]; h.ep_ret = o[29];
+    st.store(i, h);
+}
+
+__global__ void car_get_pos_kernel(CarSoA st, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    out[2 * i] = st.st[i];
+    out[2 * i + 1] = st.st[st.n + i];
+}
+
+// ---- mass properties of car.xml (density 5), same formulas as oracle/car_oracle.py -----------------------
+static void inv3(const double* m, double* o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double id = 1.0 / det;
+    o[0] = (e * i - f * h) * id; o[1] = (c * h - b * i) * id; o[2] = (b * f - c * e) * id;
+    o[3] = (f * g - d * i) * id; o[4] = (a * i - c * g) * id; o[5] = (c * d - a * f) * id;
+    o[6] = (d * h - e * g) * id; o[7] = (b * g - a * h) * id; o[8] = (a * e - b * d) * id;
+}
+
+static void add_shifted(double* J, double m, const double* Idiag, const double* d) {
+    const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            J[3 * r + c] += (r == c ? Idiag[r] + m * dd : 0.0) - m * d[r] * d[c];
+}
+
+car::Consts make_car_consts() {
+    car::Consts K{};
+    const double rho = 5.0, pi = 3.141592653589793;
+    const double boxes[5][6] = {{.1, .1, .05, 0, 0, 0},      {.1, .01, .05, 0, .15, 0},   {.01, .025, .03, 0, .125, 0},
+                                {.05, .01, .05, 0, -.165, 0}, {.05, .03, .01, 0, -.13, .04}};
+    double msum = 0, mom[3] = {0, 0, 0};
+    for (auto& b : boxes) {
+        const double m = 8 * b[0] * b[1] * b[2] * rho;
+        const double I[3] = {m / 3 * (b[1] * b[1] + b[2] * b[2]), m / 3 * (b[0] * b[0] + b[2] * b[2]),
+                             m / 3 * (b[0] * b[0] + b[1] * b[1])};
+        add_shifted(K.JO, m, I, b + 3);
+        msum += m;
+        for (int k = 0; k < 3; ++k) mom[k] += m * b[3 + k];
+    }
+    const double mw = pi * car::R_WHEEL * car::R_WHEEL * (2 * car::HALF_LEN) * rho;
+    K.I_ax = 0.5 * mw * car::R_WHEEL * car::R_WHEEL;
+    const double itr = mw * (3 * car::R_WHEEL * car::R_WHEEL + (2 * car::HALF_LEN) * (2 * car::HALF_LEN)) / 12;
+    const double mc = 4.0 / 3.0 * pi * car::R_CASTER * car::R_CASTER * car::R_CASTER * rho;
+    K.I_s = 0.4 * mc * car::R_CASTER * car::R_CASTER;
+    const double wl[3] = {-.1 - .03, .1, -.05}, wr[3] = {.1 + .03, .1, -.05}, pc[3] = {0., -.1, -.05};
+    const double Iw[3] = {K.I_ax, itr, itr}, Is[3] = {K.I_s, K.I_s, K.I_s};
+    add_shifted(K.JO, mw, Iw, wl);
+    add_shifted(K.JO, mw, Iw, wr);
+    add_shifted(K.JO, mc, Is, pc);
+    for (int k = 0; k < 3; ++k) {
+        K.posWL[k] = wl[k]; K.posWR[k] = wr[k]; K.posC[k] = pc[k];
+        mom[k] += mw * (wl[k] + wr[k]) + mc * pc[k];
+    }
+    K.mass = msum + 2 * mw + mc;
+    for (int k = 0; k < 3; ++k) K.com[k] = mom[k] / K.mass;
+    for (int variant = 0; variant < 2; ++variant) {
+        const double h = variant ? car::H : 0.0;
+        const double ka = K.I_ax / (K.I_ax + h * car::D_ROT), ks = K.I_s / (K.I_s + h * car::D_ROT);
+        double Jc[9];
+        for (int k = 0; k < 9; ++k) Jc[k] = K.JO[k];
+        Jc[0] -= 2 * ka * K.I_ax;
+        for (int k = 0; k < 3; ++k) Jc[4 * k] -= ks * K.I_s;
+        // + m [c]x [c]x = -m (|c|^2 1 - c c^T)
+        const double cc = K.com[0] * K.com[0] + K.com[1] * K.com[1] + K.com[2] * K.com[2];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Jc[3 * r + c] -= K.mass * ((r == c ? cc : 0.0) - K.com[r] * K.com[c]);
+        inv3(Jc, variant ? K.JinvH : K.Jinv0);
+    }
+    return K;
+}
+
 }  // namespace mr
 
 using namespace mr;
@@ -163,8 +324,8 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
                   mr_env** out) {
     MR_REQUIRE(out != nullptr, "out is NULL");
     MR_REQUIRE(n_envs > 0, "n_envs must be positive");
-    if (kind != MR_ENV_POINT) {
-        set_error("env kind %d is not built yet (point only)", kind);
+    if (kind != MR_ENV_POINT && kind != MR_ENV_CAR) {
+        set_error("unknown env kind %d (0 = point, 1 = car)", kind);
         return MR_ERR_UNSUPPORTED;
     }
     MR_CUDA(cudaSetDevice(device));
@@ -174,7 +335,7 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
     e->device = device;
     e->cfg.time_limit = time_limit;
     e->cfg.terminate_on_goal = terminate_on_goal ? 1 : 0;
-    size_t bytes = PointState::slab_bytes(n_envs);
+    size_t bytes = kind == MR_ENV_POINT ? PointState::slab_bytes(n_envs) : CarSoA::slab_bytes(n_envs);
     cudaError_t err = cudaMalloc(&e->slab, bytes);
     if (err != cudaSuccess) {
         set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
@@ -183,7 +344,12 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
     }
     cudaMemset(e->slab, 0, bytes);
     e->slab_bytes = bytes;
-    e->point.carve(e->slab, n_envs);
+    if (kind == MR_ENV_POINT) {
+        e->point.carve(e->slab, n_envs);
+    } else {
+        e->car.carve(e->slab, n_envs);
+        e->carK = make_car_consts();
+    }
     *out = e;
     return MR_OK;
 }
@@ -195,15 +361,27 @@ void mr_env_destroy(mr_env* env) {
     delete env;
 }
 
-int mr_env_obs_dim(const mr_env* env) { return env ? point::OBS : 0; }
-int mr_env_state_dim(const mr_env* env) { return env ? POINT_STATE_DIM : 0; }
+int mr_env_obs_dim(const mr_env* env) { return env ? (env->kind == MR_ENV_POINT ? point::OBS : car::OBS) : 0; }
+int mr_env_state_dim(const mr_env* env) {
+    return env ? (env->kind == MR_ENV_POINT ? POINT_STATE_DIM : CAR_STATE_DIM) : 0;
+}
+
+int mr_env_set_contacts(mr_env* env, int enabled) {
+    MR_REQUIRE(env, "env is NULL");
+    env->car.contacts = enabled ? 1 : 0;
+    return MR_OK;
+}
+
+static const EnvCold& cold_of(const mr_env* env) {
+    return env->kind == MR_ENV_POINT ? env->point.cold : env->car.cold;
+}
 
 int mr_env_seed(mr_env* env, const uint64_t* h_pcg_init, const uint64_t* h_pcg_goal,
                 const int64_t* h_engine_seed, void* stream) {
     MR_REQUIRE(env && h_pcg_init && h_pcg_goal && h_engine_seed, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
     MR_CUDA(cudaSetDevice(env->device));
-    const EnvCold& c = env->point.cold;
+    const EnvCold& c = cold_of(env);
     MR_CUDA(cudaMemcpyAsync(c.pcg_init, h_pcg_init, env->n * 32, cudaMemcpyHostToDevice, s));
     MR_CUDA(cudaMemcpyAsync(c.pcg_goal, h_pcg_goal, env->n * 32, cudaMemcpyHostToDevice, s));
     MR_CUDA(cudaMemcpyAsync(c.engine_seed, h_engine_seed, env->n * 8, cudaMemcpyHostToDevice, s));
@@ -213,8 +391,11 @@ int mr_env_seed(mr_env* env, const uint64_t* h_pcg_init, const uint64_t* h_pcg_g
 
 int mr_env_reset(mr_env* env, const uint8_t* mask, int first, float* obs_out, void* stream) {
     MR_REQUIRE(env, "env is NULL");
-    point_reset_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        env->point, mask, first, obs_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT)
+        point_reset_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, mask, first, obs_out);
+    else
+        car_reset_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(env->car, env->carK, mask, first, obs_out);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -222,48 +403,59 @@ int mr_env_reset(mr_env* env, const uint8_t* mask, int first, float* obs_out, vo
 int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* done,
                 uint8_t* trunc, float* term_obs, double* ep_ret, int32_t* ep_len, void* stream) {
     MR_REQUIRE(env && act && obs && rew && done && trunc, "NULL argument");
-    point_step_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        env->point, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc,
-        term_obs, ep_ret, ep_len);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT)
+        point_step_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(
+            env->point, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs, ep_ret, ep_len);
+    else
+        car_step_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(
+            env->car, env->carK, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs,
+            ep_ret, ep_len);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
 int mr_env_get_obs(mr_env* env, float* obs_out, void* stream) {
     MR_REQUIRE(env && obs_out, "NULL argument");
-    point_obs_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        env->point, obs_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT)
+        point_obs_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, obs_out);
+    else
+        car_obs_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(env->car, env->carK, obs_out);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
 int mr_env_get_state(mr_env* env, double* state_out, void* stream) {
     MR_REQUIRE(env && state_out, "NULL argument");
-    point_get_state_kernel<<<ceil_div(env->n, 128), 128, 0, (cudaStream_t)stream>>>(env->point,
-                                                                                   state_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT) point_get_state_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->point, state_out);
+    else car_get_state_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->car, state_out);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
 int mr_env_set_state(mr_env* env, const double* state_in, void* stream) {
     MR_REQUIRE(env && state_in, "NULL argument");
-    point_set_state_kernel<<<ceil_div(env->n, 128), 128, 0, (cudaStream_t)stream>>>(env->point,
-                                                                                   state_in);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT) point_set_state_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->point, state_in);
+    else car_set_state_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->car, state_in);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
 int mr_env_get_pos(mr_env* env, double* pos_out, void* stream) {
     MR_REQUIRE(env && pos_out, "NULL argument");
-    point_get_pos_kernel<<<ceil_div(env->n, 128), 128, 0, (cudaStream_t)stream>>>(env->point,
-                                                                                 pos_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->kind == MR_ENV_POINT) point_get_pos_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->point, pos_out);
+    else car_get_pos_kernel<<<ceil_div(env->n, 128), 128, 0, s>>>(env->car, pos_out);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
 int mr_env_get_reset_counts(mr_env* env, int32_t* out, void* stream) {
     MR_REQUIRE(env && out, "NULL argument");
-    MR_CUDA(cudaMemcpyAsync(out, env->point.cold.counts, env->n * 8, cudaMemcpyDeviceToDevice,
+    MR_CUDA(cudaMemcpyAsync(out, cold_of(env).counts, env->n * 8, cudaMemcpyDeviceToDevice,
                             (cudaStream_t)stream));
     return MR_OK;
 }

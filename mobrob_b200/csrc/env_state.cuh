@@ -3,6 +3,7 @@
 // coalesced.  "Hot" arrays are read+written by every step; "cold" arrays only by resets.
 #pragma once
 
+#include "env_car.cuh"
 #include "env_point.cuh"
 
 namespace mr {
@@ -78,4 +79,6 @@ struct mr_env {
     void* slab;
     size_t slab_bytes;
     mr::PointState point;
+    mr::CarSoA car;
+    mr::car::Consts carK;
 };

@@ -143,6 +143,10 @@ class GpuVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    def set_contacts(self, enabled: bool):
+        """car only: switch the floor contacts off for contact-free parity trajectories."""
+        _lib.check(self.lib.mr_env_set_contacts(self._h, int(bool(enabled))))
+
     # -- introspection ------------------------------------------------------------------------
     def get_obs_tensor(self):
         out = torch.empty_like(self.obs)
