@@ -209,6 +209,14 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream);
 
+/* Same contract as mr_rollout, built from the stand-alone kernels (policy forward, env step, two
+ * bookkeeping kernels per step).  Works for both env kinds; the car uses this path. */
+int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_obs, float* last_starts,
+                       float* obs, float* act, float* rew, float* starts, float* val, float* logp,
+                       float* last_val, uint8_t* last_done, const float* eps, uint64_t seed,
+                       uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
+                       int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

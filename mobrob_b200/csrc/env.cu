@@ -358,6 +358,7 @@ void mr_env_destroy(mr_env* env) {
     if (!env) return;
     cudaSetDevice(env->device);
     cudaFree(env->slab);
+    if (env->scratch) cudaFree(env->scratch);
     delete env;
 }
 

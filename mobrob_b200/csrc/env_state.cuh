@@ -81,4 +81,5 @@ struct mr_env {
     mr::PointState point;
     mr::CarSoA car;
     mr::car::Consts carK;
+    void* scratch = nullptr;  // lazily allocated by mr_rollout_unfused
 };

@@ -207,3 +207,98 @@ extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* la
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Unfused rollout: the same collect_rollouts semantics as mr_rollout, built from the stand-alone
+// kernels (policy forward, env step) plus two small bookkeeping kernels.  Used for the car, whose
+// contact solver is too heavy to share a warp with the MLP, and as a cross-check of the fused kernel.
+namespace mr {
+
+__global__ void noise_kernel(float* __restrict__ eps, int64_t N, uint64_t seed, uint64_t ctr, int64_t env_offset) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint64_t g = (uint64_t)(env_offset + n);
+    uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    float2 z = normal2(r.x, r.y);
+    reinterpret_cast<float2*>(eps)[n] = z;
+}
+
+// RolloutBuffer.add bookkeeping after the env step: time-out bootstrap, episode ring, start flags.
+__global__ void record_kernel(int64_t N, const float* __restrict__ rew_tmp, const uint8_t* __restrict__ done,
+                              const uint8_t* __restrict__ trunc, const float* __restrict__ term_val, float gamma,
+                              float* __restrict__ rew_out, float* __restrict__ last_starts,
+                              const double* __restrict__ ep_ret_n, const int32_t* __restrict__ ep_len_n,
+                              double* __restrict__ ep_r, int32_t* __restrict__ ep_l,
+                              unsigned long long* __restrict__ ep_count, int ring_cap) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float r = rew_tmp[n];
+    if (trunc[n]) r = __fadd_rn(r, __fmul_rn(gamma, term_val[n]));
+    rew_out[n] = r;
+    const bool d = done[n] != 0;
+    last_starts[n] = d ? 1.f : 0.f;
+    if (d) {
+        unsigned long long slot = atomicAdd(ep_count, 1ull) % (unsigned long long)ring_cap;
+        ep_r[slot] = ep_ret_n[n];
+        ep_l[slot] = ep_len_n[n];
+    }
+}
+
+}  // namespace mr
+
+extern "C" int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_obs,
+                                  float* last_starts, float* obs, float* act, float* rew, float* starts,
+                                  float* val, float* logp, float* last_val, uint8_t* last_done,
+                                  const float* eps, uint64_t seed, uint64_t noise_offset,
+                                  int64_t env_offset, double gamma, double* ep_r, int32_t* ep_l,
+                                  unsigned long long* ep_count, int ring_cap, void* stream) {
+    MR_REQUIRE(env && params && last_obs && last_starts && obs && act && rew && starts && val && logp &&
+                   last_val && last_done && ep_r && ep_l && ep_count, "NULL argument");
+    MR_REQUIRE(T > 0 && ring_cap > 0, "T and ring_cap must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t N = env->n;
+    const int O = mr_env_obs_dim(env);
+    // scratch (library-owned, one per env handle): rew_tmp f32, tv f32, eps 2 f32, done u8, trunc u8,
+    // term_obs O f32, ep_ret f64, ep_len i32, act_scratch 2 f32
+    const size_t per_env = 4 + 4 + 8 + 1 + 1 + (size_t)O * 4 + 8 + 4 + 8 + 16;
+    if (!env->scratch) {
+        MR_CUDA(cudaSetDevice(env->device));
+        MR_CUDA(cudaMalloc(&env->scratch, per_env * N + 4096));
+        MR_CUDA(cudaMemsetAsync(env->scratch, 0, per_env * N + 4096, s));
+    }
+    char* p = static_cast<char*>(env->scratch);
+    auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~size_t(255); return r; };
+    double* ep_ret_n = (double*)take(N * 8);
+    float* term_obs = (float*)take(N * O * 4);
+    float* eps_t = (float*)take(N * 8);
+    float* act_tmp = (float*)take(N * 8);
+    float* rew_tmp = (float*)take(N * 4);
+    float* tv = (float*)take(N * 4);
+    int32_t* ep_len_n = (int32_t*)take(N * 4);
+    uint8_t* done = (uint8_t*)take(N);
+    uint8_t* trunc = (uint8_t*)take(N);
+    const int tb = 256, nb = ceil_div(N, tb);
+    for (int64_t t = 0; t < T; ++t) {
+        MR_CUDA(cudaMemcpyAsync(obs + t * N * O, last_obs, N * O * 4, cudaMemcpyDeviceToDevice, s));
+        MR_CUDA(cudaMemcpyAsync(starts + t * N, last_starts, N * 4, cudaMemcpyDeviceToDevice, s));
+        const float* e = eps ? eps + t * N * 2 : eps_t;
+        if (!eps) {
+            mr::noise_kernel<<<nb, tb, 0, s>>>(eps_t, N, seed, noise_offset + (uint64_t)t, env_offset);
+            MR_CHECK_LAUNCH();
+        }
+        int rc = mr_policy_forward(params, O, last_obs, e, act + t * N * 2, logp + t * N, val + t * N, N, stream);
+        if (rc != MR_OK) return rc;
+        rc = mr_env_step(env, act + t * N * 2, last_obs, rew_tmp, done, trunc, term_obs, ep_ret_n, ep_len_n, stream);
+        if (rc != MR_OK) return rc;
+        rc = mr_policy_forward(params, O, term_obs, nullptr, act_tmp, nullptr, tv, N, stream);
+        if (rc != MR_OK) return rc;
+        mr::record_kernel<<<nb, tb, 0, s>>>(N, rew_tmp, done, trunc, tv, (float)gamma, rew + t * N, last_starts,
+                                           ep_ret_n, ep_len_n, ep_r, ep_l, ep_count, ring_cap);
+        MR_CHECK_LAUNCH();
+    }
+    int rc = mr_policy_forward(params, O, last_obs, nullptr, act_tmp, nullptr, last_val, N, stream);
+    if (rc != MR_OK) return rc;
+    MR_CUDA(cudaMemcpyAsync(last_done, done, N, cudaMemcpyDeviceToDevice, s));
+    return MR_OK;
+}

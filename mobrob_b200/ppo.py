@@ -126,6 +126,7 @@ class PPO:
         self._last_episode_starts = None
         self._xchg = None
         self.update_mode = update_mode  # "fused" | "launches" (per-minibatch kernels, NCCL when sharded)
+        self.rollout_mode = "fused"     # "fused" (point only) | "unfused" (stand-alone kernels; the car)
         self.gpu_time_ms = {}
         if env is not None:
             self.n_envs = env.num_envs
@@ -188,7 +189,9 @@ class PPO:
             self._last_obs = env.reset_tensor().clone()
             self._last_episode_starts = torch.ones(env.num_envs, dtype=torch.float32, device=self.device)
         seed = int(self.seed if self.seed is not None else 0)
-        _lib.check(self.lib.mr_rollout(
+        fused = env.env_name == "point" and self.rollout_mode == "fused"
+        fn = self.lib.mr_rollout if fused else self.lib.mr_rollout_unfused
+        _lib.check(fn(
             env._h, self.updater.params.data_ptr(), self.n_steps, self._last_obs.data_ptr(),
             self._last_episode_starts.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
             b["rewards"].data_ptr(), b["episode_starts"].data_ptr(), b["values"].data_ptr(),

@@ -102,3 +102,47 @@ def test_car_vec_env_on_the_floor(cuda_lib):
         assert np.linalg.norm(r[15:17]) < 1.0
     # the car rests on its wheels: body height a fraction of a millimetre below the 0.1 m rest pose
     assert np.all(np.abs(got[:, 2] - 0.1) < 5e-3)
+
+
+def test_car_ppo_iteration_and_pretrained_policy(cuda_lib, golden_dir):
+    """(a) collect_rollouts for the car (unfused kernels) replayed through the oracle step by step;
+    (b) one PPO update runs on the 26-dim observation; (c) the shipped car policy drives the CUDA car
+    to its goals (functional check of the contact model: the reference trained it on real MuJoCo)."""
+    import os
+    import sys
+
+    from mobrob_b200 import GpuVecEnv
+    from mobrob_b200.ppo import PPO
+    from oracle import sb3_oracle
+
+    n, T, seed = 6, 24, 1
+    env = GpuVecEnv("car", n, seed=None, time_limit=1000, terminate_on_goal=True)
+    model = PPO("MlpPolicy", env, n_steps=T, batch_size=48, n_epochs=2, gae_lambda=0.5, ent_coef=0.05, seed=seed)
+    w = dict(np.load(os.path.join(golden_dir, "car_policy.npz")))
+    model.policy.load_state_dict({k: torch.as_tensor(v) for k, v in w.items()})
+    ref_pol = sb3_oracle.MlpPolicyOracle(26).load_numpy(w)
+    venv = GoalVecOracle(co.CarBody(n), seed=seed, time_limit=1000, terminate_on_goal=True)
+    obs_ref = venv.reset()
+    eps = torch.randn((T, n, 2), generator=torch.Generator().manual_seed(3))
+    model.collect_rollouts(eps.cuda().contiguous())
+    torch.cuda.synchronize()
+    b = {k: v.cpu().numpy() for k, v in model.buf.items()}
+    for t in range(T):
+        np.testing.assert_allclose(b["obs"][t], obs_ref, rtol=1e-4, atol=1e-4, err_msg=f"obs t={t}")
+        with torch.no_grad():
+            a_ref, v_ref, lp_ref = ref_pol.forward_with_noise(torch.as_tensor(b["obs"][t]), eps[t])
+        assert np.abs(b["actions"][t] - a_ref.numpy()).max() <= 1e-5 * max(1.0, float(a_ref.abs().max()))
+        np.testing.assert_allclose(b["values"][t], v_ref.numpy(), rtol=1e-5, atol=1e-5)
+        obs_ref, rew, done, info = venv.step(np.clip(b["actions"][t], -1, 1))
+        np.testing.assert_allclose(b["rewards"][t], rew, rtol=1e-4, atol=1e-5)
+    p0 = model.updater.params.clone()
+    model.train()
+    torch.cuda.synchronize()
+    assert torch.isfinite(model.updater.params).all() and float((model.updater.params - p0).abs().max()) > 0
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import eval_policy
+
+    res = eval_policy.evaluate_gpu(os.path.join(golden_dir, "policies", "car-ppo.zip"), 512, steps=600, env_name="car")
+    print("car policy:", {k: v for k, v in res.items() if not k.startswith("first_l") and k != "first_ok"})
+    assert res["first_goal_success_rate"] > 0.5

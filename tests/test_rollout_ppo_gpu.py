@@ -198,3 +198,21 @@ def test_pretrained_point_policy_reaches_goals(cuda_lib, golden_dir):
     assert (g["first_len"] == o["first_len"]).mean() > 0.6
     big = eval_policy.evaluate_gpu(z, 4096, steps=400)
     assert abs(big["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.03
+
+
+def test_unfused_rollout_equals_fused(cuda_lib, golden_dir):
+    """mr_rollout (one launch) and mr_rollout_unfused (stand-alone kernels) are the same computation."""
+    outs = []
+    for mode in ("fused", "unfused"):
+        model, _, _ = _setup(golden_dir, 40, 96, 4, 30, False, batch_size=64)
+        model.policy.state_dict()["log_std"].fill_(2.0)
+        model.rollout_mode = mode
+        model.collect_rollouts()
+        model.collect_rollouts()
+        torch.cuda.synchronize()
+        model._drain_episodes()
+        outs.append(({k: v.clone() for k, v in model.buf.items()}, model._episode_num, model._last_obs.clone()))
+    for k in outs[0][0]:
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    assert outs[0][1] == outs[1][1] > 0
+    assert torch.equal(outs[0][2], outs[1][2])

@@ -16,12 +16,12 @@ import numpy as np
 import torch
 
 
-def evaluate_gpu(zip_path, n, horizon=1000, seed=0, steps=None):
+def evaluate_gpu(zip_path, n, horizon=1000, seed=0, steps=None, env_name="point"):
     from mobrob_b200 import GpuVecEnv
     from mobrob_b200.ppo import PPO
 
     model = PPO.load(zip_path)
-    env = GpuVecEnv("point", n, seed=seed, time_limit=horizon, terminate_on_goal=True)
+    env = GpuVecEnv(env_name, n, seed=seed, time_limit=horizon, terminate_on_goal=True)
     obs = env.reset_tensor()
     steps = steps or horizon
     first_len = torch.zeros(n, dtype=torch.int32, device=env.device)
@@ -85,8 +85,11 @@ if __name__ == "__main__":
     ap.add_argument("--zip", default=os.path.join(ROOT, "tests", "golden", "policies", "point-ppo.zip"))
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--oracle-n", type=int, default=0)
+    ap.add_argument("--env", default="point")
     a = ap.parse_args()
-    out = {"gpu": evaluate_gpu(a.zip, a.n)}
+    if a.env != "point" and "point-ppo" in a.zip:
+        a.zip = a.zip.replace("point-ppo", f"{a.env}-ppo")
+    out = {"gpu": evaluate_gpu(a.zip, a.n, env_name=a.env)}
     if a.oracle_n:
         out["oracle"] = evaluate_oracle(a.zip, a.oracle_n)
         g = evaluate_gpu(a.zip, a.oracle_n)
