@@ -13,7 +13,9 @@
 //   * each CTA writes one partial gradient; ppo_reduce_kernel sums the partials in a fixed
 //     order (deterministic), adam_kernel clips by global norm and applies torch's Adam.
 #include "mlp.cuh"
+#include "ppo_tc.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace mr {
@@ -442,16 +444,52 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int
     grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)blockIdx.x * grad_stride(O));
 }
 
+// Tensor-core version (ppo_tc.cuh): even CTAs own the policy tower, odd CTAs the value tower.
+template <int KP>
+__global__ void __launch_bounds__(tc::THREADS, 1) ppo_grad_tc_kernel(GradArgs A, int O) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    tc::Ctx C = tc::make_ctx(smem_raw, blockIdx.x & 1);
+    tc::setup(C);
+    tc::stage<KP>(C, A.params, O);
+    __syncthreads();
+    tc::minibatch<KP>(C, A, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
+    tc::teardown(C);
+}
+
 // grad[p] = sum over CTAs; finishes the scalar terms.  One thread per parameter; the n_parts
 // loads are independent, so they are issued 8 deep into 4 interleaved accumulators that are
 // combined in a fixed order (deterministic for a given n_parts).
 __global__ void __launch_bounds__(128)
 ppo_reduce_kernel(const float* __restrict__ partials, int n_parts, int O, float ent_coef,
-                  const double* __restrict__ mb_stats, float* __restrict__ grad, float rank_share) {
+                  const double* __restrict__ mb_stats, float* __restrict__ grad, float rank_share, int towers) {
     const int stride = grad_stride(O);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= stride) return;
     const float* src = partials + p;
+    if (towers) {  // tensor-core kernel: CTA b holds tower (b & 1) only
+        src += (size_t)tc::param_tower(p, make_layout(O)) * stride;
+        n_parts >>= 1;
+        // consecutive parts of one tower are 2 rows apart
+        const int st2 = 2 * stride;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int b = 0;
+        for (; b + 8 <= n_parts; b += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (size_t)(b + q) * st2);
+            a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+            a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+        }
+        for (; b < n_parts; ++b) a0 += __ldg(src + (size_t)b * st2);
+        float s = (a0 + a1) + (a2 + a3);
+        const ParamLayout L = make_layout(O);
+        const int sb = stat_base(O);
+        if (p >= L.logstd && p < L.logstd + ACT) s -= ent_coef * rank_share;
+        if (p >= sb && p < sb + 4) s *= (float)(1.0 / mb_stats[2]);
+        if (p >= sb + 4 || (p >= L.total && p < sb)) s = 0.f;
+        grad[p] = s;
+        return;
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int b = 0;
     for (; b + 8 <= n_parts; b += 8) {
@@ -643,8 +681,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
 }
 
-template <int O_PAD>
+template <int O_PAD, bool TC>
 __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, int O) {
+    static_assert(PG_THREADS == tc::THREADS, "both gradient paths use 256 threads");
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_grp[PG_THREADS];
     __shared__ double s_dred[PG_WARPS];
@@ -660,16 +699,30 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
     unsigned target = 0;
     int64_t step = E.step[0];
     const float omb1 = 1.f - E.beta1, omb2 = 1.f - E.beta2;
+    tc::Ctx C;
+    if constexpr (TC) {
+        C = tc::make_ctx(reinterpret_cast<uint8_t*>(smem), c & 1);
+        tc::setup(C);
+    }
+    // partial gradients of parameter p: every CTA (SIMT) or the CTAs of p's tower (tensor-core path)
+    const int n_src = TC ? G >> 1 : G;
+    const size_t src_step = TC ? 2 * (size_t)stride : (size_t)stride;
 
     for (int64_t m = 0; m < n_mb; ++m) {
-        GradSmem S = grad_stage<O_PAD>(smem, E.params, O, m == 0);
-        __syncthreads();
         GradArgs A = E.G;
         A.params = E.params;
         A.perm = E.G.perm + m * E.batch;
         A.mb_size = min(E.batch, E.n_samples - m * E.batch);
         A.mb_stats = E.stats + 3 * m;
-        grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)c * stride);
+        if constexpr (TC) {
+            tc::stage<O_PAD>(C, E.params, O);
+            __syncthreads();
+            tc::minibatch<O_PAD>(C, A, O, A.partials + (size_t)c * stride);
+        } else {
+            GradSmem S = grad_stage<O_PAD>(smem, E.params, O, m == 0);
+            __syncthreads();
+            grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)c * stride);
+        }
         grid_barrier(E.barrier, target, G);
 
         // ---- phase B: this CTA's slice of the gradient --------------------------------------------
@@ -682,17 +735,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
         const int p = p0 + j;
         float part = 0.f;
         if (g < groups && p < stride) {
-            const float* src = A.partials + p;
+            const float* src = A.partials + p + (TC ? (size_t)tc::param_tower(p, L) * stride : 0);
             float a0 = 0.f, a1 = 0.f;
             int b = g;
-            for (; b + 7 * groups < G; b += 8 * groups) {
+            for (; b + 7 * groups < n_src; b += 8 * groups) {
                 float v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(b + q * groups) * stride);
+                for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(b + q * groups) * src_step);
                 a0 += v[0]; a1 += v[1]; a0 += v[2]; a1 += v[3];
                 a0 += v[4]; a1 += v[5]; a0 += v[6]; a1 += v[7];
             }
-            for (; b < G; b += groups) a0 += __ldcg(src + (size_t)b * stride);
+            for (; b < n_src; b += groups) a0 += __ldcg(src + (size_t)b * src_step);
             part = a0 + a1;
         }
         s_grp[tid] = part;
@@ -779,6 +832,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
         grid_barrier(E.barrier, target, G);
     }
     if (c == 0 && tid == 0) E.step[0] = step;
+    if constexpr (TC) tc::teardown(C);
+}
+
+// The tensor-core kernels are the product path; MR_PPO_SIMT=1 selects the fp32 CUDA-core kernels
+// (kept as a cross-check of the tcgen05 path in the tests).
+static bool use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MR_PPO_SIMT");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 static size_t grad_smem_bytes(int O, int O_PAD) {
@@ -829,15 +894,28 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
     if (!attr_set) {
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         attr_set = true;
     }
     static int max_parts = 0;
     if (!max_parts) max_parts = mr_ppo_max_parts();
-    const int64_t tiles = (mb_size + PG_S - 1) / PG_S;
-    const int grid = (int)std::min<int64_t>(tiles, max_parts);
     cudaStream_t s = (cudaStream_t)stream;
-    if (o_pad == 16) ppo_grad_kernel<16><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
-    else ppo_grad_kernel<32><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
+    int grid;
+    if (use_tc()) {
+        MR_REQUIRE(obs_dim < 32 && max_parts >= 2, "tensor-core path needs obs_dim < 32");
+        // obs_dim + 1 (bias column) padded to the bf16 MMA K of 16
+        const int kp = obs_dim + 1 <= 16 ? 16 : 32;
+        const int64_t tiles = (mb_size + tc::TILE - 1) / tc::TILE;
+        grid = (int)std::min<int64_t>(2 * tiles, max_parts & ~1);
+        if (kp == 16) ppo_grad_tc_kernel<16><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(A, obs_dim);
+        else ppo_grad_tc_kernel<32><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(A, obs_dim);
+    } else {
+        const int64_t tiles = (mb_size + PG_S - 1) / PG_S;
+        grid = (int)std::min<int64_t>(tiles, max_parts);
+        if (o_pad == 16) ppo_grad_kernel<16><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
+        else ppo_grad_kernel<32><<<grid, PG_THREADS, smem, s>>>(A, obs_dim);
+    }
     MR_CHECK_LAUNCH();
     if (n_parts) *n_parts = grid;
     return MR_OK;
@@ -855,7 +933,7 @@ int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float*
     if (rc != MR_OK) return rc;
     const int stride = grad_stride(obs_dim);
     ppo_reduce_kernel<<<ceil_div(stride, 128), 128, 0, (cudaStream_t)stream>>>(
-        partials, grid, obs_dim, ent_coef, mb_stats, grad, rank_share);
+        partials, grid, obs_dim, ent_coef, mb_stats, grad, rank_share, use_tc() ? 1 : 0);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -990,17 +1068,22 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
         E.seq0 = xchg->seq;
         xchg->seq += (unsigned)n_mb;
     }
-    const int o_pad = obs_dim <= 16 ? 16 : 32;
-    const size_t smem = grad_smem_bytes(obs_dim, o_pad);
+    const bool tcp = use_tc();
+    MR_REQUIRE(!tcp || ((n_cta & 1) == 0 && obs_dim < 32), "tensor-core path needs an even CTA count and obs_dim < 32");
+    const int o_pad = tcp ? (obs_dim + 1 <= 16 ? 16 : 32) : (obs_dim <= 16 ? 16 : 32);
+    const size_t smem = tcp ? (size_t)tc::SMEM_BYTES : grad_smem_bytes(obs_dim, o_pad);
     static bool attr_set = false;
     if (!attr_set) {
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         attr_set = true;
     }
     int O = obs_dim;
     void* args[] = {&E, &O};
-    const void* fn = o_pad == 16 ? (const void*)ppo_epoch_kernel<16> : (const void*)ppo_epoch_kernel<32>;
+    const void* fn = tcp ? (o_pad == 16 ? (const void*)ppo_epoch_kernel<16, true> : (const void*)ppo_epoch_kernel<32, true>)
+                         : (o_pad == 16 ? (const void*)ppo_epoch_kernel<16, false> : (const void*)ppo_epoch_kernel<32, false>);
     MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(PG_THREADS), args, smem, s));
     mr::count_launch();
     return MR_OK;
