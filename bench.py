@@ -255,10 +255,10 @@ def run_ours(args):
 
     # ---- e2e: the public API (PPOCtrl.learn) with SB3's host-side permutations (pinned H2D) and
     #      per-iteration D2H of the training statistics / episode buffer ---------------------------------
-    model.host_permutation = True
+    model.permutation = "pool"   # host-drawn permutations (permfeed.py), pinned -> device every epoch
     model.verbose = 0
     barrier()
-    model.learn(total_timesteps=steps_per_iter * world, reset_num_timesteps=True)  # warm
+    model.learn(total_timesteps=steps_per_iter * world * 3, reset_num_timesteps=True)  # warm (logger paths too)
     barrier()
     t0 = time.perf_counter()
     model.learn(total_timesteps=steps_per_iter * world * args.steps, reset_num_timesteps=True)
@@ -286,8 +286,9 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world,
-                    "what": "PPOCtrl.learn(): host np.random.permutation per epoch copied from pinned memory, "
-                            "logger + episode-buffer reads every iteration"},
+                    "what": "PPOCtrl.learn(): minibatch permutations drawn on the host (thread pool, one "
+                            "iteration ahead) and copied from pinned memory every epoch; logger + episode-buffer "
+                            "reads (D2H) every iteration"},
             "roofline": roofline, "roofline_env_step": env_roof}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)

@@ -217,6 +217,13 @@ int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_
                        uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
                        int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
 
+/* Host-side minibatch index stream (no device work): out[0..n) <- a uniformly random permutation
+ * of 0..n-1, a pure function of (seed, stream).  Replaces, for throughput runs, the
+ * np.random.permutation call of [SB3 2.0.0] RolloutBuffer.get (reached from
+ * src/mobrob/rl_control/ppo.py:73-74); the bit-for-bit numpy stream stays available on the Python
+ * side (PPO(permutation="sb3")).  Thread-safe; `out` is host memory (pinned or pageable). */
+int mr_host_permutation(uint64_t seed, uint64_t stream, int64_t n, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ _SIGNATURES = {
                                      c_float, c_float, c_float, c_int, _P, _P, _P]),
     "mr_rollout_unfused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,
                                    c_uint64, c_int64, c_double, _P, _P, _P, c_int, _P]),
+    "mr_host_permutation": (c_int, [c_uint64, c_uint64, c_int64, _P]),
     "mr_adam_step": (c_int, [_P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float,
                              _P, _P]),
 }
@@ -70,7 +71,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("MR_LIB_PATH", _build.LIB_PATH)  # MR_LIB_PATH: debug variants (tools/trace_epoch.py)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: run `python -m mobrob_b200.build` (or __graft_entry__.build()). "

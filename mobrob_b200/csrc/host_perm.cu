@@ -1,0 +1,98 @@
+// Host-side minibatch permutation: the part of [SB3 2.0.0] RolloutBuffer.get that stays on the host
+// (``indices = np.random.permutation(n_envs * n_steps)``, reached from
+// src/mobrob/rl_control/ppo.py:73-74), written so that it keeps up with a B200: numpy's
+// Fisher-Yates costs ~20 ns per index at n = 1.2e6 (one dependent cache miss per swap), ten
+// epochs of that are longer than the whole device iteration.
+//
+// Scatter shuffle (Rao-Sandelius): deal the indices into 2^k buckets with uniform random keys
+// (sequential writes), then Fisher-Yates inside each bucket (cache resident).  Dealing
+// independently and shuffling every bucket uniformly yields a uniformly distributed permutation.
+// The stream is xoshiro256** seeded by splitmix64 from (seed, stream): a pure function of its
+// arguments, independent of thread count.  Plain host code; no device work.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct Xoshiro {
+    uint64_t s[4];
+    static uint64_t splitmix(uint64_t& x) {
+        uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    Xoshiro(uint64_t seed, uint64_t stream) {
+        uint64_t x = seed ^ (stream * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull);
+        for (int i = 0; i < 4; ++i) s[i] = splitmix(x);
+    }
+    static inline uint64_t rotl(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
+    inline uint64_t next() {
+        const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+    // unbiased integer in [0, bound), bound < 2^32 (Lemire's multiply-shift with rejection)
+    inline uint32_t below(uint32_t bound) {
+        uint64_t m = (uint64_t)(uint32_t)next() * bound;
+        uint32_t lo = (uint32_t)m;
+        if (lo < bound) {
+            const uint32_t thresh = (0u - bound) % bound;
+            while (lo < thresh) {
+                m = (uint64_t)(uint32_t)next() * bound;
+                lo = (uint32_t)m;
+            }
+        }
+        return (uint32_t)(m >> 32);
+    }
+};
+
+}  // namespace
+
+extern "C" int mr_host_permutation(uint64_t seed, uint64_t stream, int64_t n, int64_t* out) {
+    MR_REQUIRE(out != nullptr, "NULL argument");
+    MR_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "n out of range");
+    if (n == 0) return MR_OK;
+    Xoshiro g(seed, stream);
+    // buckets of ~8K indices (32 KB as uint32: L1/L2 resident)
+    int bits = 0;
+    while ((n >> bits) > 8192 && bits < 12) ++bits;
+    const int K = 1 << bits;
+    std::vector<uint32_t> tmp((size_t)n);
+    if (K > 1) {
+        std::vector<uint8_t> key8;
+        std::vector<uint16_t> key((size_t)n);
+        std::vector<int64_t> count(K + 1, 0);
+        for (int64_t i = 0; i < n;) {   // 64 random bits -> up to 5 keys of <= 12 bits
+            uint64_t r = g.next();
+            for (int q = 0; q < 5 && i < n; ++q, ++i, r >>= 12) {
+                const uint16_t b = (uint16_t)(r & (uint64_t)(K - 1));
+                key[(size_t)i] = b;
+                ++count[b + 1];
+            }
+        }
+        for (int b = 0; b < K; ++b) count[b + 1] += count[b];
+        std::vector<int64_t> head(count.begin(), count.end() - 1);
+        for (int64_t i = 0; i < n; ++i) tmp[(size_t)head[key[(size_t)i]]++] = (uint32_t)i;
+        for (int b = 0; b < K; ++b) {
+            uint32_t* a = tmp.data() + count[b];
+            const int64_t len = count[b + 1] - count[b];
+            for (int64_t i = len - 1; i > 0; --i) {
+                const uint32_t j = g.below((uint32_t)i + 1);
+                const uint32_t t = a[i]; a[i] = a[j]; a[j] = t;
+            }
+        }
+    } else {
+        for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = (uint32_t)i;
+        for (int64_t i = n - 1; i > 0; --i) {
+            const uint32_t j = g.below((uint32_t)i + 1);
+            const uint32_t t = tmp[(size_t)i]; tmp[(size_t)i] = tmp[j]; tmp[j] = t;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)tmp[(size_t)i];
+    return MR_OK;
+}

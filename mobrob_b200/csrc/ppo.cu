@@ -448,11 +448,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_grad_kernel(GradArgs A, int
 template <int KP>
 __global__ void __launch_bounds__(tc::THREADS, 1) ppo_grad_tc_kernel(GradArgs A, int O) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    MR_TR(0);
     tc::Ctx C = tc::make_ctx(smem_raw, blockIdx.x & 1);
     tc::setup(C);
     tc::stage<KP>(C, A.params, O);
+    const tc::Sched S{A.mb_size, A.mb_size, 1, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1)};
+    tc::Pipe<KP> Q;
+    tc::pipe_start<KP>(Q, A, S, O, threadIdx.x & 127, threadIdx.x >> 7, C.tower == 0);
     __syncthreads();
-    tc::minibatch<KP>(C, A, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
+    tc::minibatch<KP>(C, A, S, A.mb_stats, 0, Q, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
     tc::teardown(C);
 }
 
@@ -681,9 +685,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
 }
 
-template <int O_PAD, bool TC>
+template <int O_PAD>
 __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, int O) {
     static_assert(PG_THREADS == tc::THREADS, "both gradient paths use 256 threads");
+    constexpr bool TC = false;   // fp32 CUDA-core cross-check path; the product path is ppo_epoch_tc_kernel
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_grp[PG_THREADS];
     __shared__ double s_dred[PG_WARPS];
@@ -699,11 +704,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
     unsigned target = 0;
     int64_t step = E.step[0];
     const float omb1 = 1.f - E.beta1, omb2 = 1.f - E.beta2;
-    tc::Ctx C;
-    if constexpr (TC) {
-        C = tc::make_ctx(reinterpret_cast<uint8_t*>(smem), c & 1);
-        tc::setup(C);
-    }
     // partial gradients of parameter p: every CTA (SIMT) or the CTAs of p's tower (tensor-core path)
     const int n_src = TC ? G >> 1 : G;
     const size_t src_step = TC ? 2 * (size_t)stride : (size_t)stride;
@@ -714,16 +714,13 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
         A.perm = E.G.perm + m * E.batch;
         A.mb_size = min(E.batch, E.n_samples - m * E.batch);
         A.mb_stats = E.stats + 3 * m;
-        if constexpr (TC) {
-            tc::stage<O_PAD>(C, E.params, O);
-            __syncthreads();
-            tc::minibatch<O_PAD>(C, A, O, A.partials + (size_t)c * stride);
-        } else {
+        {
             GradSmem S = grad_stage<O_PAD>(smem, E.params, O, m == 0);
             __syncthreads();
             grad_minibatch<O_PAD>(A, O, S, A.partials + (size_t)c * stride);
         }
         grid_barrier(E.barrier, target, G);
+        MR_TR(4);
 
         // ---- phase B: this CTA's slice of the gradient --------------------------------------------
         ++step;
@@ -800,7 +797,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
             for (int w = 0; w < PG_WARPS; ++w) t += s_dred[w];
             E.sq[c] = t;
         }
+        MR_TR(5);
         grid_barrier(E.barrier, target, G);
+        MR_TR(6);
 
         // ---- phase C: global-norm clip + Adam on the slice ----------------------------------------------
         if (tid < 32) {
@@ -829,10 +828,203 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
             if (c == 0 && tid == 0) { row[0] = total_norm; row[1] = coef; row[2] = (float)step; row[3] = 0.f; }
             if (own && p >= sb && p < sb + 4) row[4 + p - sb] = val;
         }
+        MR_TR(7);
         grid_barrier(E.barrier, target, G);
+        MR_TR(8);
     }
     if (c == 0 && tid == 0) E.step[0] = step;
-    if constexpr (TC) tc::teardown(C);
+}
+
+// Tensor-core epoch kernel.  Per minibatch: tiles (tc::minibatch, rows prefetched one tile ahead)
+// -> grid barrier -> 16-byte slice reduction of the partial gradients [-> NVLink all-reduce] ->
+// grid barrier -> global-norm clip + Adam on the slice -> grid barrier -> tc::restage.
+// Every hand-off through L2 is one wave of independent 8/16-byte loads: with all 148 SMs pulling
+// at once a round trip costs 1400-2900 cycles (tools/ubench/l2_handoff.cu), so the phases are
+// shaped to pay it once each.  (Tried and measured slower: every CTA applying Adam to its whole
+// tower to save the third barrier -- 4 x the L2 traffic, 15 us instead of 10 us per minibatch.)
+template <int KP>
+__global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs E, int O) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ float4 s_grp[tc::THREADS];
+    const ParamLayout L = make_layout(O);
+    const int tid = threadIdx.x;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int stride = grad_stride(O), sb = stat_base(O), n_params = L.total;
+    const int slice = (((stride + G - 1) / G) + 3) & ~3;
+    const int q4 = slice >> 2;                          // 16-byte lanes per slice (<= 32, checked on the host)
+    const int groups = tc::THREADS / q4;                // part-groups summing in parallel
+    const int p0 = c * slice;
+    const int n_mb = (int)((E.n_samples + E.batch - 1) / E.batch);
+    const int n_src = G >> 1;
+    const int rot = c % n_src;
+    unsigned target = 0;
+    int64_t step = E.step[0];
+    double b1pow = pow((double)E.beta1, (double)step), b2pow = pow((double)E.beta2, (double)step);
+
+    MR_TR(0);
+    tc::Ctx C = tc::make_ctx(smem_raw, c & 1);
+    tc::setup(C);
+    GradArgs A = E.G;
+    const tc::Sched S{E.n_samples, E.batch, n_mb, c >> 1, G >> 1};
+    tc::Pipe<KP> Q;
+    tc::pipe_start<KP>(Q, A, S, O, tid & 127, tid >> 7, C.tower == 0);
+
+    tc::stage<KP>(C, E.params, O);
+    __syncthreads();
+
+    for (int m = 0; m < n_mb; ++m) {
+        MR_TR(2);
+        tc::minibatch<KP>(C, A, S, E.stats, m, Q, O, A.partials + (size_t)c * stride);
+        MR_TR(3);
+        grid_barrier(E.barrier, target, G);
+        MR_TR(4);
+
+        // ---- this CTA's slice of the gradient: sum over the CTAs of each parameter's tower -----------
+        ++step;
+        b1pow *= (double)E.beta1;   // beta^step, carried from one pow() per launch
+        b2pow *= (double)E.beta2;
+        const int j = tid % q4, g = tid / q4;
+        const int p = p0 + 4 * j;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < groups && p < stride) {
+            const int t0 = tc::param_tower(p, L), t3 = tc::param_tower(p + 3, L);
+            const bool s1 = tc::param_tower(p + 1, L) != 0, s2 = tc::param_tower(p + 2, L) != 0;
+            const size_t step4 = 2 * (size_t)stride;
+            if (t0 == t3 && s1 == (t0 != 0) && s2 == (t0 != 0)) {
+                const float* src = A.partials + (size_t)t0 * stride + p;
+                for (int b0 = g; b0 < n_src; b0 += groups) {
+                    int b = b0 + rot;   // CTAs start on different rows: no L2 hot spot
+                    b = b >= n_src ? b - n_src : b;
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * step4));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            } else {  // the quad straddles a tower boundary: pick per element
+                const float* src = A.partials + p;
+                for (int b0 = g; b0 < n_src; b0 += groups) {
+                    int b = b0 + rot;
+                    b = b >= n_src ? b - n_src : b;
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * step4));
+                    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * step4 + stride));
+                    acc.x += t0 ? v1.x : v0.x;
+                    acc.y += s1 ? v1.y : v0.y;
+                    acc.z += s2 ? v1.z : v0.z;
+                    acc.w += t3 ? v1.w : v0.w;
+                }
+            }
+        }
+        MR_TR(30);
+        s_grp[tid] = acc;
+        __syncthreads();
+        MR_TR(31);
+        const bool own = tid < q4 && p < stride;
+        float val[4] = {0.f, 0.f, 0.f, 0.f};
+        if (own) {
+            for (int q = 0; q < groups; ++q) {
+                const float4 v = s_grp[q * q4 + j];
+                val[0] += v.x; val[1] += v.y; val[2] += v.z; val[3] += v.w;
+            }
+            const float share = E.rank_share ? E.rank_share[m] : 1.f;
+            const float inv_cnt = (float)(1.0 / E.stats[3 * m + 2]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pe = p + e;
+                if (pe >= L.logstd && pe < L.logstd + ACT) val[e] -= E.G.ent_coef * share;
+                if (pe >= sb && pe < sb + 4) val[e] *= inv_cnt;
+                if (pe >= sb + 4 || (pe >= n_params && pe < sb)) val[e] = 0.f;
+            }
+        }
+        if (E.X.world > 1 && own) {
+            // one-shot all-reduce over NVLink peer memory, tagged 8-byte packets (see ppo_epoch_kernel)
+            const unsigned seq = E.seq0 + (unsigned)m + 1u;
+            const int slot = seq & 1u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned long long pkt =
+                    ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(val[e]);
+                for (int r = 0; r < E.X.world; ++r)
+                    if (r != E.X.rank)
+                        __stcg(E.X.peer_inbox[r] + ((size_t)slot * E.X.world + E.X.rank) * stride + p + e, pkt);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float tot = 0.f;
+                for (int r = 0; r < E.X.world; ++r) {  // rank order: bit-identical on every rank
+                    if (r == E.X.rank) { tot += val[e]; continue; }
+                    const unsigned long long* src = E.X.inbox + ((size_t)slot * E.X.world + r) * stride + p + e;
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                    } while ((unsigned)(v >> 32) != seq);
+                    tot += __uint_as_float((unsigned)v);
+                }
+                val[e] = tot;
+            }
+        }
+        MR_TR(32);
+        double sq = 0.0;
+        if (own) {
+            *reinterpret_cast<float4*>(E.grad + p) = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (p + e < n_params) sq += (double)val[e] * (double)val[e];
+        }
+        if (tid < 32) {   // own threads all sit in warp 0 (q4 <= 32)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (tid == 0) E.sq[c] = sq;
+        }
+        MR_TR(5);
+        grid_barrier(E.barrier, target, G);
+        MR_TR(6);
+
+        // ---- global-norm clip + Adam on the slice (torch's single-tensor arithmetic, as adam_kernel) ---
+        if (tid < 32) {
+            double t = 0.0;
+            for (int b = tid; b < G; b += 32) t += __ldcg(E.sq + b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const float total_norm = (float)sqrt(t);
+            const float coef = fminf(E.max_grad_norm / (total_norm + 1e-6f), 1.0f);
+            if (own && p < n_params) {   // p is 4-aligned; n_params is not: the last quad is partial
+                const float neg_step_size = (float)(-(double)E.lr / (1.0 - b1pow));
+                const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
+                const float omb1 = 1.f - E.beta1, omb2 = 1.f - E.beta2;
+                const float4 m4 = __ldcg(reinterpret_cast<const float4*>(E.exp_avg + p));
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(E.exp_avg_sq + p));
+                const float4 w4 = __ldcg(reinterpret_cast<const float4*>(E.params + p));
+                float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float gq = __fmul_rn(val[e], coef);
+                    const float mq = __fadd_rn(__fmul_rn(mm[e], E.beta1), __fmul_rn(gq, omb1));
+                    const float vq = __fadd_rn(__fmul_rn(vv[e], E.beta2), __fmul_rn(__fmul_rn(gq, gq), omb2));
+                    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vq), bc2_sqrt), E.eps);
+                    const float nw = __fadd_rn(ww[e], __fdiv_rn(__fmul_rn(neg_step_size, mq), denom));
+                    const bool ok = p + e < n_params;
+                    mm[e] = ok ? mq : mm[e]; vv[e] = ok ? vq : vv[e]; ww[e] = ok ? nw : ww[e];
+                }
+                *reinterpret_cast<float4*>(E.exp_avg + p) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                *reinterpret_cast<float4*>(E.exp_avg_sq + p) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                *reinterpret_cast<float4*>(E.params + p) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+            }
+            if (E.info) {
+                float* row = E.info + 8 * m;
+                if (c == 0 && tid == 0) { row[0] = total_norm; row[1] = coef; row[2] = (float)step; row[3] = 0.f; }
+                if (own && p == sb) { row[4] = val[0]; row[5] = val[1]; row[6] = val[2]; row[7] = val[3]; }
+            }
+        }
+        MR_TR(7);
+        grid_barrier(E.barrier, target, G);
+        MR_TR(8);
+        if (m + 1 < n_mb) {
+            tc::restage<KP>(C, E.params, O);
+            __syncthreads();   // misc floats are read at the top of the next minibatch
+        }
+        MR_TR(37);
+    }
+    if (c == 0 && tid == 0) E.step[0] = step;
+    tc::teardown(C);
 }
 
 // The tensor-core kernels are the product path; MR_PPO_SIMT=1 selects the fp32 CUDA-core kernels
@@ -970,6 +1162,20 @@ int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     return MR_OK;
 }
 
+#ifdef MR_TRACE
+// debug build only: copy out and clear the phase trace of CTA `cta` (0 or 1); returns the count
+int mr_trace_read(int cta, unsigned long long* out, int cap) {
+    unsigned n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, mr::g_trace_n, sizeof(unsigned), cta * sizeof(unsigned));
+    if ((int)n > cap) n = cap;
+    cudaMemcpyFromSymbol(out, mr::g_trace, n * sizeof(unsigned long long), (size_t)cta * 4096 * sizeof(unsigned long long));
+    unsigned z = 0;
+    cudaMemcpyToSymbol(mr::g_trace_n, &z, sizeof(unsigned), cta * sizeof(unsigned));
+    return (int)n;
+}
+#endif
+
 struct mr_xchg {
     int world, rank, device, n_cta;
     int64_t stride;
@@ -1074,16 +1280,21 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     const size_t smem = tcp ? (size_t)tc::SMEM_BYTES : grad_smem_bytes(obs_dim, o_pad);
     static bool attr_set = false;
     if (!attr_set) {
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         attr_set = true;
+    }
+    if (tcp) {
+        MR_REQUIRE(n_samples < (int64_t(1) << 31), "tensor-core path indexes samples with 32 bits");
+        const int stride = grad_stride(obs_dim);
+        MR_REQUIRE((((stride + n_cta - 1) / n_cta + 3) >> 2) <= 32, "gradient slice per CTA too wide");
     }
     int O = obs_dim;
     void* args[] = {&E, &O};
-    const void* fn = tcp ? (o_pad == 16 ? (const void*)ppo_epoch_kernel<16, true> : (const void*)ppo_epoch_kernel<32, true>)
-                         : (o_pad == 16 ? (const void*)ppo_epoch_kernel<16, false> : (const void*)ppo_epoch_kernel<32, false>);
+    const void* fn = tcp ? (o_pad == 16 ? (const void*)ppo_epoch_tc_kernel<16> : (const void*)ppo_epoch_tc_kernel<32>)
+                         : (o_pad == 16 ? (const void*)ppo_epoch_kernel<16> : (const void*)ppo_epoch_kernel<32>);
     MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(PG_THREADS), args, smem, s));
     mr::count_launch();
     return MR_OK;

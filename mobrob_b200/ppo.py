@@ -87,7 +87,7 @@ class PPO:
                  normalize_advantage=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, use_sde=False,
                  sde_sample_freq=-1, target_kl=None, stats_window_size=100, tensorboard_log=None,
                  policy_kwargs=None, verbose=0, seed=None, device="auto", _init_setup_model=True,
-                 host_permutation=True, update_mode="fused"):
+                 host_permutation=None, update_mode="fused", permutation=None):
         if policy not in ("MlpPolicy", MlpPolicy):
             raise ValueError("only MlpPolicy is built (the only policy mobrob uses)")
         if use_sde or clip_range_vf is not None or target_kl is not None:
@@ -107,7 +107,18 @@ class PPO:
         self.normalize_advantage, self.ent_coef, self.vf_coef = normalize_advantage, ent_coef, vf_coef
         self.max_grad_norm, self.verbose, self.seed = max_grad_norm, verbose, seed
         self.tensorboard_log = tensorboard_log
-        self.host_permutation = host_permutation  # True: np.random.permutation like SB3 (H2D per epoch)
+        # RolloutBuffer.get's index stream: "sb3" = np.random.permutation on the global MT19937
+        # (bit-for-bit SB3, serial on the host); "pool" = host threads drawing PCG64 streams keyed by
+        # (seed, iteration, epoch) one iteration ahead (permfeed.py); "device" = torch.randperm.
+        if permutation is None:
+            permutation = "sb3" if host_permutation in (None, True) else "device"
+        if permutation not in ("sb3", "pool", "device"):
+            raise ValueError(f"Unknown permutation mode: {permutation}")
+        self.permutation = permutation
+        self._feeder = None
+        self._train_count = 0
+        self._train_stats = None
+        self._snap = None
         self._stats_window_size = stats_window_size
         self.num_timesteps = 0
         self._total_timesteps = 0
@@ -211,25 +222,75 @@ class PPO:
         d = _dist()
         return d.get_world_size() if d is not None else 1
 
-    def _drain_episodes(self):
-        """Monitor's ep_info_buffer: read the finished episodes of the last rollout (one D2H)."""
-        total = int(self.ep_count.item())
-        new = min(total - self._ep_seen, EP_RING)
+    def _snapshot_async(self):
+        """Enqueue the D2H reads one logging step needs -- Monitor's newest episodes (ep_info_buffer),
+        the previous train()'s statistics -- into pinned memory; returns the event to wait for.
+        Nothing here blocks the host: train() of this iteration is enqueued behind it."""
+        W = self._stats_window_size
+        if getattr(self, "_snap", None) is None:
+            self._snap = dict(count=torch.zeros(1, dtype=torch.int64).pin_memory(),
+                              r=torch.zeros(W, dtype=torch.float64).pin_memory(),
+                              l=torch.zeros(W, dtype=torch.int32).pin_memory(),
+                              train=torch.zeros(12, dtype=torch.float32).pin_memory())
+        sn = self._snap
+        idx = (self.ep_count - W + torch.arange(W, device=self.device)).clamp_(min=0) % EP_RING
+        sn["count"].copy_(self.ep_count, non_blocking=True)
+        sn["r"].copy_(self.ep_r[idx], non_blocking=True)
+        sn["l"].copy_(self.ep_l[idx], non_blocking=True)
+        if self._train_stats is not None:
+            sn["train"].copy_(self._train_stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def _drain_episodes(self, ev=None):
+        """Monitor's ep_info_buffer from the last snapshot (waits for its event)."""
+        if ev is None:
+            ev = self._snapshot_async()
+        ev.synchronize()
+        sn, W = self._snap, self._stats_window_size
+        total = int(sn["count"][0])
+        new = min(total - self._ep_seen, W, total)
         if new > 0:
-            idx = (torch.arange(total - new, total, device=self.device) % EP_RING)
-            r = self.ep_r[idx].cpu().numpy()
-            l = self.ep_l[idx].cpu().numpy()
+            r, l = sn["r"].numpy(), sn["l"].numpy()
             now = round(time.time() - self.env.t_start, 6)
-            for i in range(max(0, new - self._stats_window_size), new):
+            for i in range(W - new, W):
                 self.ep_info_buffer.append({"r": round(float(r[i]), 6), "l": int(l[i]), "t": now})
         self._ep_seen = total
         self._episode_num = total
 
     # -- update --------------------------------------------------------------------------------------
-    def _permutation(self, n):
-        if self.host_permutation:  # RolloutBuffer.get: np.random.permutation on the global MT19937
-            return torch.as_tensor(np.random.permutation(n).astype(np.int64)).pin_memory().to(
-                self.device, non_blocking=True)
+    @property
+    def host_permutation(self):
+        return self.permutation != "device"
+
+    @host_permutation.setter
+    def host_permutation(self, flag):
+        self.permutation = "sb3" if flag else "device"
+
+    def _get_feeder(self):
+        if self._feeder is None:
+            from .permfeed import PermutationFeeder
+
+            d = _dist()
+            self._feeder = PermutationFeeder(self.n_steps * self.env.num_envs, self.n_epochs, self.device,
+                                             seed=int(self.seed or 0), rank=d.get_rank() if d is not None else 0)
+        return self._feeder
+
+    def _permutation(self, n, epoch=0):
+        if self.permutation == "pool":
+            return self._get_feeder().get(self._train_count, epoch)
+        if self.permutation == "sb3":  # RolloutBuffer.get: np.random.permutation on the global MT19937
+            if getattr(self, "_pin", None) is None or self._pin.numel() != n:
+                self._pin = torch.empty(n, dtype=torch.int64).pin_memory()
+                self._pin_ev = None
+            if self._pin_ev is not None:
+                self._pin_ev.synchronize()
+            self._pin.numpy()[:] = np.random.permutation(n)
+            out = self._pin.to(self.device, non_blocking=True)
+            self._pin_ev = torch.cuda.Event()
+            self._pin_ev.record(torch.cuda.current_stream(self.device))
+            return out
         return torch.randperm(n, device=self.device, dtype=torch.int64)
 
     def train(self, perms=None):
@@ -244,7 +305,7 @@ class PPO:
         log = torch.zeros((self.n_epochs * n_mb, 8), dtype=torch.float32, device=self.device)
         k = 0
         for epoch in range(self.n_epochs):
-            perm = perms[epoch] if perms is not None else self._permutation(n)
+            perm = perms[epoch] if perms is not None else self._permutation(n, epoch)
             if not torch.is_tensor(perm):
                 perm = torch.as_tensor(np.asarray(perm, dtype=np.int64))
             perm = perm.to(self.device).contiguous()
@@ -271,27 +332,40 @@ class PPO:
                     d.all_reduce(up.grad)
                     up.adam_step(log[k])
                     k += 1
+        if perms is None and self.permutation == "pool":
+            self._feeder.release(self._train_count)
+        self._train_count += 1
         self._n_updates += self.n_epochs
         self._train_log = (log[:, 4:], log[:, :4])
-
-    def _log_train(self):
-        tails, log = self._train_log
-        t = tails.mean(dim=0).cpu().numpy()
-        b = self.buf
+        # logger inputs, computed on the device behind the last epoch (read one iteration later):
+        # [0:4] mean policy_loss / value_loss / clip_fraction / approx_kl, [4:6] last minibatch's
+        # policy and value loss, [6] explained variance of the buffer this update trained on,
+        # [7:9] log_std after the update
+        tails = log[:, 4:]
         y_pred, y_true = b["values"].flatten(), b["returns"].flatten()
         var_y = torch.var(y_true)
-        ev = float("nan") if float(var_y) == 0 else float(1 - torch.var(y_true - y_pred) / var_y)
-        ls = self.policy.state_dict()["log_std"]
-        ent = -float((0.5 + 0.5 * np.log(2 * np.pi) + ls).sum())
+        ev = torch.where(var_y == 0, torch.full_like(var_y, float("nan")), 1 - torch.var(y_true - y_pred) / var_y)
+        st = torch.zeros(12, dtype=torch.float32, device=self.device)
+        st[0:4] = tails.mean(dim=0)
+        st[4:6] = tails[-1, 0:2]
+        st[6] = ev
+        st[7:9] = self.policy.state_dict()["log_std"]
+        self._train_stats = st
+
+    def _log_train(self):
+        """train/* keys of SB3's PPO.train, from the statistics snapshot of the previous update."""
+        t = self._snap["train"].numpy()
+        ls_h = t[7:9].astype(np.float64)
+        ent = -float((0.5 + 0.5 * np.log(2 * np.pi) + ls_h).sum())
         lg = self.logger
         lg.record("train/entropy_loss", ent)
         lg.record("train/policy_gradient_loss", float(t[0]))
         lg.record("train/value_loss", float(t[1]))
         lg.record("train/approx_kl", float(t[3]))
         lg.record("train/clip_fraction", float(t[2]))
-        lg.record("train/loss", float(tails[-1, 0] + self.ent_coef * ent + self.vf_coef * tails[-1, 1]))
-        lg.record("train/explained_variance", ev)
-        lg.record("train/std", float(ls.exp().mean()))
+        lg.record("train/loss", float(t[4] + self.ent_coef * ent + self.vf_coef * t[5]))
+        lg.record("train/explained_variance", float(t[6]))
+        lg.record("train/std", float(np.exp(ls_h).mean()))
         lg.record("train/n_updates", self._n_updates)
         lg.record("train/clip_range", self.clip_range)
         lg.record("train/learning_rate", self.learning_rate)
@@ -321,6 +395,10 @@ class PPO:
                 bar = None
         while self.num_timesteps < self._total_timesteps:
             before = self.num_timesteps
+            if self.permutation == "pool":  # copies of this iteration overlap the rollout; next one is drawn
+                f = self._get_feeder()
+                f.stage(self._train_count)
+                f.prefetch(self._train_count + 1)
             self.collect_rollouts()
             if callback is not None and hasattr(callback, "on_rollout_steps"):
                 if callback.on_rollout_steps(self.n_steps) is False:
@@ -328,8 +406,14 @@ class PPO:
             iteration += 1
             if bar is not None:
                 bar.update(self.num_timesteps - before)
-            if log_interval is not None and iteration % log_interval == 0:
-                self._drain_episodes()
+            log_now = log_interval is not None and iteration % log_interval == 0
+            had_update = self._train_stats is not None
+            # SB3 logs, then trains.  Here the update is ENQUEUED first and the host formats the log
+            # while the GPU works; the logged numbers are the same (snapshot taken before train()).
+            ev = self._snapshot_async() if log_now else None
+            self.train()
+            if log_now:
+                self._drain_episodes(ev)
                 elapsed = max((time.time_ns() - self.start_time) / 1e9, sys.float_info.epsilon)
                 fps = int((self.num_timesteps - self._num_timesteps_at_start) / elapsed)
                 lg = self.logger
@@ -340,13 +424,12 @@ class PPO:
                 lg.record("time/iterations", iteration)
                 lg.record("time/time_elapsed", int(elapsed))
                 lg.record("time/total_timesteps", self.num_timesteps)
-                if iteration > 1:
+                if had_update:
                     self._log_train()
                 if self._is_rank0():
                     lg.dump(self.num_timesteps)
                 else:
                     lg.name_to_value = {}
-            self.train()
         if bar is not None:
             bar.close()
         if callback is not None and hasattr(callback, "on_training_end"):
