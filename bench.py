@@ -31,7 +31,7 @@ N_EPOCHS = 10
 METRIC = "env-steps/sec (rollout+PPO update), point env"
 WORKLOAD = "point env 4096 parallel envs/GPU full rollout + GAE + PPO update (BASELINE.json configs[2])"
 
-# algorithmic work of the dominant kernel (ppo_grad_kernel), DESIGN.md "Kernels":
+# algorithmic work of the dominant kernel (ppo_epoch_tc_kernel), DESIGN.md "Kernels":
 # per sample and epoch: forward + backward-data + backward-weight of both 14-64-64 towers
 FLOP_PER_SAMPLE_EPOCH = 61056  # SURVEY.md section 8d, point
 ENV_STEP_BYTES = 145           # SURVEY.md section 8d, stand-alone point env-step
@@ -240,17 +240,26 @@ def run_ours(args):
     ev[2].record()
     barrier()
     rollout_ms, train_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    grad_ms = time_grad_kernel(model, dev)
+    epoch_ms = time_epoch_kernel(model, dev)
     peaks, peaks_src = measured_peaks()
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-    achieved = FLOP_PER_SAMPLE_EPOCH * BATCH / (grad_ms * 1e-3) / 1e12
-    roofline = {"kernel": "ppo_grad_kernel<16>", "bound": "fp32",
-                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None, "ms_per_launch": grad_ms,
-                "peak_source": f"148 SM x 128 FP32 lanes x 2 x clocks.max.sm ({peaks_src} MEASURED_PEAKS.json clock); "
-                               "SIMT fp32 FMA kernel: 1e-5 gradient parity rules out bf16/tf32 tensor math",
-                "frac_of_bf16_tensor_peak": achieved / peaks.get("bf16_tflops", 1590.0),
-                "step_share": {"rollout_ms": rollout_ms, "update_ms": train_ms}}
+    tensor_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone
+    achieved = FLOP_PER_SAMPLE_EPOCH * steps_per_iter / (epoch_ms * 1e-3) / 1e12
+    roofline = {"kernel": "ppo_epoch_tc_kernel<16> (one launch = one epoch = 64 minibatch updates: tcgen05 forward/"
+                          "backward GEMMs, gradient reduction, clip, Adam)",
+                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES, "ms_per_launch": epoch_ms,
+                "algorithmic": f"{FLOP_PER_SAMPLE_EPOCH} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples per launch",
+                "peak_source": f"bf16_tflops of MEASURED_PEAKS.json ({peaks_src})",
+                "tensor_flops_issued_per_algorithmic_flop": 6,
+                "frac_issued": 6 * achieved / tensor_peak,
+                "frac_of_fp32_fma_peak": achieved / fp32_peak,
+                "note": "fp32 products are formed from three bf16 parts per operand (6 MMAs per product, 1e-5 gradient "
+                        "parity), so 6x the algorithmic FLOPs go through the tensor pipe; the kernel is bound by the "
+                        "per-minibatch dependency chain (3 grid barriers + L2 hand-offs), see profiles/",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/ (per launch)",
+                "step_share": {"rollout_ms": rollout_ms, "update_ms": train_ms,
+                               "epoch_kernel_ms_x_epochs": epoch_ms * N_EPOCHS}}
     env_roof = time_env_step_kernel(dev, peaks)
 
     # ---- e2e: the public API (PPOCtrl.learn) with SB3's host-side permutations (pinned H2D) and
@@ -300,25 +309,33 @@ def run_ours(args):
 EP_D2H_BYTES = 100 * 12 + 8
 
 
-def time_grad_kernel(model, dev):
-    """Average duration of ppo_grad_kernel alone (no reduce / Adam), CUDA events on the launching stream."""
+# dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
+EPOCH_KERNEL_DRAM_BYTES = 162.2e6
+
+
+def time_epoch_kernel(model, dev):
+    """Average duration of the epoch kernel alone, CUDA events on the launching stream.  Parameters
+    and Adam state are restored afterwards (the launches are real updates)."""
     import torch
 
     up, b = model.updater, model.buf
     T, N = model.n_steps, model.env.num_envs
+    saved = [t.clone() for t in (up.params, up.exp_avg, up.exp_avg_sq, up.step)]
     perm = torch.randperm(T * N, device=dev, dtype=torch.int64)
     stats = up.adv_stats(b["advantages"], perm, BATCH, N, T)
-    n_mb = T * N // BATCH
-    for mb in range(3):
-        up.compute_partials(b, perm[mb * BATCH:(mb + 1) * BATCH], stats[mb], N, T)
+    for _ in range(2):
+        up.train_epoch_fused(b, perm, stats, BATCH, N, T)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
     e0.record()
-    for mb in range(n_mb):
-        up.compute_partials(b, perm[mb * BATCH:(mb + 1) * BATCH], stats[mb], N, T)
+    for _ in range(reps):
+        up.train_epoch_fused(b, perm, stats, BATCH, N, T)
     e1.record()
     torch.cuda.synchronize(dev)
-    return e0.elapsed_time(e1) / n_mb
+    for t, sv in zip((up.params, up.exp_avg, up.exp_avg_sq, up.step), saved):
+        t.copy_(sv)
+    return e0.elapsed_time(e1) / reps
 
 
 def time_env_step_kernel(dev, peaks):

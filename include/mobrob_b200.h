@@ -217,6 +217,11 @@ int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_
                        uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
                        int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
 
+/* Device-side minibatch index stream: out[0..n) <- a keyed pseudo-random permutation of 0..n-1
+ * (a pure function of (seed, stream_id); one thread per index, no sort).  For runs that keep
+ * RolloutBuffer.get's indices on the device (PPO(permutation="device")). */
+int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* out, void* stream);
+
 /* Host-side minibatch index stream (no device work): out[0..n) <- a uniformly random permutation
  * of 0..n-1, a pure function of (seed, stream).  Replaces, for throughput runs, the
  * np.random.permutation call of [SB3 2.0.0] RolloutBuffer.get (reached from

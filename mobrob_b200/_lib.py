@@ -55,6 +55,7 @@ _SIGNATURES = {
                                      c_float, c_float, c_float, c_int, _P, _P, _P]),
     "mr_rollout_unfused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,
                                    c_uint64, c_int64, c_double, _P, _P, _P, c_int, _P]),
+    "mr_device_permutation": (c_int, [c_uint64, c_uint64, c_int64, _P, _P]),
     "mr_host_permutation": (c_int, [c_uint64, c_uint64, c_int64, _P]),
     "mr_adam_step": (c_int, [_P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float,
                              _P, _P]),

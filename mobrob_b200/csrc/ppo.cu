@@ -598,21 +598,33 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(AdamArgs A) {
 // Per-minibatch advantage sums of one epoch's permutation: stats[mb] = (sum, sum of squares,
 // count) in float64 (shifted by the first element to keep the variance well conditioned is not
 // needed at float64).  One CTA per minibatch.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm,
                  int64_t n_samples, int64_t batch, int64_t N, int64_t T,
                  double* __restrict__ stats) {
     const int64_t mb = blockIdx.x;
     const int64_t s0 = mb * batch, s1 = min(n_samples, s0 + batch);
     double s = 0.0, q = 0.0;
-    for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
-        int64_t id = perm[i];
-        int64_t n = id / T, t = id - n * T;
-        double a = (double)adv[t * N + n];
-        s += a;
-        q += a * a;
+    constexpr int U = 4;   // independent gathers in flight per thread
+    for (int64_t i0 = s0 + threadIdx.x; i0 < s1; i0 += (int64_t)U * blockDim.x) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            a[u] = 0.f;
+            if (i < s1) {
+                const int64_t id = perm[i];
+                const int64_t n = id / T, t = id - n * T;
+                a[u] = __ldg(adv + t * N + n);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s += (double)a[u];
+            q += (double)a[u] * (double)a[u];
+        }
     }
-    __shared__ double sh[2][8];
+    __shared__ double sh[2][32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -622,11 +634,37 @@ adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm
     __syncthreads();
     if (threadIdx.x == 0) {
         double ts = 0, tq = 0;
-        for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += sh[0][w]; tq += sh[1][w]; }
         stats[3 * mb] = ts;
         stats[3 * mb + 1] = tq;
         stats[3 * mb + 2] = (double)(s1 - s0);
     }
+}
+
+// Device-side index stream for RolloutBuffer.get when the permutation need not come from the host:
+// out[i] = P(i), P a keyed bijection of [0, n) -- four rounds of (odd multiply, xor-shift, add key)
+// on the enclosing power-of-two domain, cycle-walked back into range.  One thread per index, no
+// sort (torch.randperm costs 0.17 ms per epoch at n = 1.2e6; this is a 10 MB store).
+struct PermKey {
+    uint32_t mul[4], add[4];
+    int bits;
+};
+__device__ __forceinline__ uint32_t perm_mix(uint32_t x, const PermKey& K) {
+    const uint32_t mask = K.bits >= 32 ? 0xFFFFFFFFu : ((1u << K.bits) - 1u);
+    const int sh = (K.bits + 1) >> 1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        x = (x * K.mul[r] + K.add[r]) & mask;
+        x ^= x >> sh;
+    }
+    return x;
+}
+__global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ out, int64_t n, PermKey K) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = (uint32_t)i;
+    do { x = perm_mix(x, K); } while ((int64_t)x >= n);
+    out[i] = (int64_t)x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1064,7 +1102,28 @@ int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, i
     MR_REQUIRE(adv && perm && stats, "NULL argument");
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     int n_mb = ceil_div(n_samples, batch_size);
-    adv_stats_kernel<<<n_mb, 256, 0, (cudaStream_t)stream>>>(adv, perm, n_samples, batch_size, N, T, stats);
+    adv_stats_kernel<<<n_mb, 1024, 0, (cudaStream_t)stream>>>(adv, perm, n_samples, batch_size, N, T, stats);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* out, void* stream) {
+    MR_REQUIRE(out != nullptr, "NULL argument");
+    MR_REQUIRE(n > 0 && n < (int64_t(1) << 31), "n out of range");
+    PermKey K;
+    K.bits = 1;
+    while ((int64_t(1) << K.bits) < n) ++K.bits;
+    uint64_t x = seed ^ (stream_id * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull);
+    for (int r = 0; r < 4; ++r) {   // splitmix64 key schedule
+        uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        K.mul[r] = (uint32_t)z | 1u;            // odd: invertible modulo 2^bits
+        K.mul[r] = (K.mul[r] & ~6u) | 4u;       // = 5 (mod 8): full-period style multiplier
+        K.add[r] = (uint32_t)(z >> 32);
+    }
+    device_perm_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, K);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }

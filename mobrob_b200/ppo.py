@@ -109,7 +109,7 @@ class PPO:
         self.tensorboard_log = tensorboard_log
         # RolloutBuffer.get's index stream: "sb3" = np.random.permutation on the global MT19937
         # (bit-for-bit SB3, serial on the host); "pool" = host threads drawing PCG64 streams keyed by
-        # (seed, iteration, epoch) one iteration ahead (permfeed.py); "device" = torch.randperm.
+        # (seed, iteration, epoch) one iteration ahead (permfeed.py); "device" = mr_device_permutation.
         if permutation is None:
             permutation = "sb3" if host_permutation in (None, True) else "device"
         if permutation not in ("sb3", "pool", "device"):
@@ -291,7 +291,14 @@ class PPO:
             self._pin_ev = torch.cuda.Event()
             self._pin_ev.record(torch.cuda.current_stream(self.device))
             return out
-        return torch.randperm(n, device=self.device, dtype=torch.int64)
+        # "device": keyed bijection computed by one kernel (no sort)
+        if getattr(self, "_dperm", None) is None or self._dperm.numel() != n:
+            self._dperm = torch.empty(n, dtype=torch.int64, device=self.device)
+        out = self._dperm
+        d = _dist()
+        key = ((d.get_rank() if d is not None else 0) << 48) ^ (self._train_count << 16) ^ epoch
+        _lib.check(self.lib.mr_device_permutation(int(self.seed or 0), key, n, out.data_ptr(), self._stream()))
+        return out
 
     def train(self, perms=None):
         """PPO.train: n_epochs passes of minibatch updates.  perms: optional list of int64 index
