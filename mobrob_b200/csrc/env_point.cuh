@@ -92,7 +92,8 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     h.cx = fminf(fmaxf(a0, -1.f), 1.f);  // engine.py:1401-1405
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
     const double prevx = h.d.px, prevy = h.d.py;  // _prev_pos == position before the step
-    point::substeps(h.d, (double)h.cx, (double)h.cz);
+    double hc, hs;  // cos / sin of the heading after the step
+    point::substeps(h.d, (double)h.cx, (double)h.cz, hc, hs);
     const double gx = (double)h.gx, gy = (double)h.gy;
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.d.px, h.d.py);
@@ -108,7 +109,7 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
-    point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
+    point::sensors_cs(h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
     if (r.done) {
 #pragma unroll
         for (int k = 0; k < point::OBS; ++k) term_obs[k] = obs[k];

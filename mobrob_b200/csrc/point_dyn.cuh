@@ -48,7 +48,8 @@ __device__ __forceinline__ double clampd(double x, double lo, double hi) {
 }
 
 // (M + h D)^-1 (Q_act - D qdot - C) by the Schur complement on the hinge (B^2 + C^2 = (mc)^2
-// is constant, so both pivots are compile-time constants).  c, s = cos/sin of the heading.
+// is constant, so both pivots -- and their reciprocals -- are compile-time constants: the solve
+// is multiplications only).  c, s = cos/sin of the heading.
 template <bool IMPLICIT>
 __device__ __forceinline__ void accel(double c, double s, double vx, double vy, double om,
                                       double f, double cz, double& ax, double& ay, double& al) {
@@ -56,24 +57,42 @@ __device__ __forceinline__ void accel(double c, double s, double vx, double vy, 
     constexpr double A = MASS + h * D_SLIDE;
     constexpr double DTH = I_O + h * D_HINGE;
     constexpr double SCHUR = DTH - MC * MC / A;
+    constexpr double INV_A = 1.0 / A, INV_SCHUR = 1.0 / SCHUR, MC_A = MC / A;
     double tau = GEAR * clampd(cz - GEAR * om, -FLIM, FLIM);  // velocity servo, kv = 1
     double w2 = om * om;
     double r0 = f * c - D_SLIDE * vx + MC * c * w2;
     double r1 = f * s - D_SLIDE * vy + MC * s * w2;
     double r2 = tau - D_HINGE * om;
-    double t = MC * (-s * r0 + c * r1) / A;
-    al = (r2 - t) / SCHUR;
-    ax = (r0 + MC * s * al) / A;
-    ay = (r1 - MC * c * al) / A;
+    double t = MC_A * (c * r1 - s * r0);
+    al = (r2 - t) * INV_SCHUR;
+    ax = (r0 + MC * s * al) * INV_A;
+    ay = (r1 - MC * c * al) * INV_A;
 }
 
-// Engine.step physics: ctrl already clipped to [-1, 1].
-__device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
+// (c, s) <- rotation of (c, s) by the small angle a: Taylor series of sin / cos (|a| < 0.02 ->
+// truncation below 1e-18), so the heading's sine / cosine follow the integrator without a
+// trigonometric call per substep.  Large steps (never reached: |omega| stays below ~4 rad/s) fall
+// back to the exact evaluation at the new heading.
+__device__ __forceinline__ void rotate_cs(double& c, double& s, double a, double psi_new) {
+    if (fabs(a) < 0.02) {
+        const double x = a * a;
+        const double sd = a * (1.0 + x * (-1.0 / 6.0 + x * (1.0 / 120.0 + x * (-1.0 / 5040.0))));
+        const double cd = 1.0 + x * (-0.5 + x * (1.0 / 24.0 + x * (-1.0 / 720.0 + x * (1.0 / 40320.0))));
+        const double c2 = c * cd - s * sd;
+        s = s * cd + c * sd;
+        c = c2;
+    } else {
+        sincos(psi_new, &s, &c);
+    }
+}
+
+// Engine.step physics: ctrl already clipped to [-1, 1].  Returns cos / sin of the final heading
+// (one exact sincos at the start of the env step, ten incremental rotations).
+__device__ __forceinline__ void substeps(Dyn& d, double cx, double cz, double& c, double& s) {
     const double f = GEAR * clampd(cx, -FLIM, FLIM);  // site motor along body x
+    sincos(d.psi, &s, &c);
 #pragma unroll 1
     for (int k = 0; k < FRAME_SKIP; ++k) {
-        double s, c;
-        sincos(d.psi, &s, &c);
         double ax, ay, al;
         accel<true>(c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
         d.vx += H * ax;
@@ -81,17 +100,22 @@ __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
         d.om += H * al;
         d.px += H * d.vx;
         d.py += H * d.vy;
-        d.psi += H * d.om;
+        const double a = H * d.om;
+        d.psi += a;
+        rotate_cs(c, s, a, d.psi);
     }
+}
+__device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
+    double c, s;
+    substeps(d, cx, cz, c, s);
 }
 
 // Engine.obs(): mj_forward at the current state with the current ctrl; sorted-key layout
 // [accelerometer 0:3 | goal_compass 3:5 | gyro 5:8 | magnetometer 8:11 | velocimeter 11:14].
-__device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
-                                        float* o) {
+// c, s = cos / sin of d.psi.
+__device__ __forceinline__ void sensors_cs(const Dyn& d, double c, double s, double cx, double cz, float gx,
+                                           float gy, float* o) {
     const double f = GEAR * clampd(cx, -FLIM, FLIM);
-    double s, c;
-    sincos(d.psi, &s, &c);
     double ax, ay, al;
     accel<false>(c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
     o[0] = (float)(c * ax + s * ay);
@@ -111,6 +135,12 @@ __device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, floa
     o[11] = (float)(c * d.vx + s * d.vy);
     o[12] = (float)(-s * d.vx + c * d.vy);
     o[13] = 0.f;
+}
+__device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
+                                        float* o) {
+    double s, c;
+    sincos(d.psi, &s, &c);
+    sensors_cs(d, c, s, cx, cz, gx, gy, o);
 }
 
 // ||a - b|| exactly as numpy evaluates it on two-vectors (no contraction): the reached flag

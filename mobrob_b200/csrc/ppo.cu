@@ -910,7 +910,35 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
     tc::stage<KP>(C, E.params, O);
     __syncthreads();
 
+    // this CTA's slice of the fp32 master copy and the Adam moments lives in registers of the
+    // `own` threads for the whole epoch (nobody else writes it): no load on the critical path
+    const int own_p = p0 + 4 * (tid % q4);
+    const bool own_t = tid < q4 && own_p < stride && own_p < n_params;
+    // (the arrays hold n_params floats, which is not a multiple of 4: the last quad is partial)
+    auto load4 = [&](const float* a) {
+        if (own_p + 3 < n_params) return *reinterpret_cast<const float4*>(a + own_p);
+        float4 r = make_float4(a[own_p], 0.f, 0.f, 0.f);
+        if (own_p + 1 < n_params) r.y = a[own_p + 1];
+        if (own_p + 2 < n_params) r.z = a[own_p + 2];
+        return r;
+    };
+    auto store4 = [&](float* a, const float4& r) {
+        if (own_p + 3 < n_params) { *reinterpret_cast<float4*>(a + own_p) = r; return; }
+        a[own_p] = r.x;
+        if (own_p + 1 < n_params) a[own_p + 1] = r.y;
+        if (own_p + 2 < n_params) a[own_p + 2] = r.z;
+    };
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = m4, w4 = m4;
+    if (own_t) {
+        m4 = load4(E.exp_avg);
+        v4 = load4(E.exp_avg_sq);
+        w4 = load4(E.params);
+    }
+
     for (int m = 0; m < n_mb; ++m) {
+        // inputs of the reduction that do not depend on other CTAs: fetched ahead of the barrier
+        const float share = E.rank_share ? __ldg(E.rank_share + m) : 1.f;
+        const float inv_cnt = (float)(1.0 / __ldg(E.stats + 3 * m + 2));
         MR_TR(2);
         tc::minibatch<KP>(C, A, S, E.stats, m, Q, O, A.partials + (size_t)c * stride);
         MR_TR(3);
@@ -961,8 +989,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                 const float4 v = s_grp[q * q4 + j];
                 val[0] += v.x; val[1] += v.y; val[2] += v.z; val[3] += v.w;
             }
-            const float share = E.rank_share ? E.rank_share[m] : 1.f;
-            const float inv_cnt = (float)(1.0 / E.stats[3 * m + 2]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int pe = p + e;
@@ -1028,9 +1054,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                 const float neg_step_size = (float)(-(double)E.lr / (1.0 - b1pow));
                 const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
                 const float omb1 = 1.f - E.beta1, omb2 = 1.f - E.beta2;
-                const float4 m4 = __ldcg(reinterpret_cast<const float4*>(E.exp_avg + p));
-                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(E.exp_avg_sq + p));
-                const float4 w4 = __ldcg(reinterpret_cast<const float4*>(E.params + p));
                 float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1042,9 +1065,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                     const bool ok = p + e < n_params;
                     mm[e] = ok ? mq : mm[e]; vv[e] = ok ? vq : vv[e]; ww[e] = ok ? nw : ww[e];
                 }
-                *reinterpret_cast<float4*>(E.exp_avg + p) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-                *reinterpret_cast<float4*>(E.exp_avg_sq + p) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                *reinterpret_cast<float4*>(E.params + p) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+                m4 = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                v4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                w4 = make_float4(ww[0], ww[1], ww[2], ww[3]);
+                store4(E.params, w4);   // read by every CTA of the tower (restage)
             }
             if (E.info) {
                 float* row = E.info + 8 * m;
@@ -1060,6 +1084,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
             __syncthreads();   // misc floats are read at the top of the next minibatch
         }
         MR_TR(37);
+    }
+    if (own_t) {
+        store4(E.exp_avg, m4);
+        store4(E.exp_avg_sq, v4);
     }
     if (c == 0 && tid == 0) E.step[0] = step;
     tc::teardown(C);

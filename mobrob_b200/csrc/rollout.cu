@@ -13,10 +13,17 @@
 #include "env_state.cuh"
 #include "mlp.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace mr {
 
-constexpr int RO_WARPS = 4;
-constexpr int RO_E = 8;
+// (warps per CTA, environments per warp): measured on B200 at 4096 envs x 296 steps (tools/time_rollout.py):
+// 4x8 2.55 ms, 7x4 2.19 ms, 8x4 2.06 ms, 4x4 2.04 ms, 14x4 3.09 ms.  4 x 4 = 256 CTAs, ~7 warps per SM
+// (the env step is a long fp64 dependency chain: more, smaller warps
+// hide it better than 4 x 8, at the price of re-reading the weights per 4 instead of 8 samples).
+constexpr int RO_WARPS_DEFAULT = 4;
+constexpr int RO_E_DEFAULT = 4;
 
 struct RolloutArgs {
     PointState st;
@@ -45,6 +52,7 @@ struct RolloutArgs {
     int ring_cap;
 };
 
+template <int RO_WARPS, int RO_E>
 __global__ void __launch_bounds__(RO_WARPS * 32) point_rollout_kernel(RolloutArgs A) {
     extern __shared__ __align__(16) float smem[];
     const int O = A.O;
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) point_rollout_kernel(RolloutArg
             a = __fadd_rn(out, __fmul_rn(sig, z));
             lp = normal_logprob(a, out, sig);
         }
-        const int src = 3 * (lane & 7);
+        const int src = 3 * (lane % RO_E);
         const float a0 = __shfl_sync(0xffffffffu, a, src);
         const float a1 = __shfl_sync(0xffffffffu, a, src + 1);
         const float v = __shfl_sync(0xffffffffu, out, src + 2);
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) point_rollout_kernel(RolloutArg
 
     // values of the final observation, carry-over state
     const float out = warp_mlp_forward<RO_E>(W, O, obsT, hbuf, lane);
-    const float v_last = __shfl_sync(0xffffffffu, out, 3 * (lane & 7) + 2);
+    const float v_last = __shfl_sync(0xffffffffu, out, 3 * (lane % RO_E) + 2);
     if (phys) {
         A.last_val[n] = v_last;
         A.last_done[n] = done_flag ? 1 : 0;
@@ -169,6 +177,43 @@ __global__ void __launch_bounds__(RO_WARPS * 32) point_rollout_kernel(RolloutArg
 }  // namespace mr
 
 using namespace mr;
+
+template <int RO_WARPS, int RO_E>
+static int launch_rollout_cfg(const RolloutArgs& A, int64_t n_envs, cudaStream_t stream) {
+    const size_t smem = (smem_w_floats(A.O) + RO_WARPS * (MAX_OBS * RO_E + 128 * RO_E)) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA(cudaFuncSetAttribute(point_rollout_kernel<RO_WARPS, RO_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     100 * 1024));
+        attr_set = true;
+    }
+    const int64_t warps = (n_envs + RO_E - 1) / RO_E;
+    const int blocks = (int)((warps + RO_WARPS - 1) / RO_WARPS);
+    point_rollout_kernel<RO_WARPS, RO_E><<<blocks, RO_WARPS * 32, smem, stream>>>(A);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+static int launch_rollout(const RolloutArgs& A, int64_t n_envs, cudaStream_t stream) {
+    static int cfg = -1;   // MR_ROLLOUT_CFG = "<warps>x<envs per warp>" selects a tuning variant
+    if (cfg < 0) {
+        const char* e = getenv("MR_ROLLOUT_CFG");
+        cfg = 0;
+        if (e) {
+            if (!strcmp(e, "4x8")) cfg = 1;
+            else if (!strcmp(e, "4x4")) cfg = 2;
+            else if (!strcmp(e, "8x4")) cfg = 3;
+            else if (!strcmp(e, "14x4")) cfg = 4;
+        }
+    }
+    switch (cfg) {
+        case 1: return launch_rollout_cfg<4, 8>(A, n_envs, stream);
+        case 2: return launch_rollout_cfg<4, 4>(A, n_envs, stream);
+        case 3: return launch_rollout_cfg<8, 4>(A, n_envs, stream);
+        case 4: return launch_rollout_cfg<14, 4>(A, n_envs, stream);
+        default: return launch_rollout_cfg<RO_WARPS_DEFAULT, RO_E_DEFAULT>(A, n_envs, stream);
+    }
+}
 
 extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* last_obs,
                           float* last_starts, float* obs, float* act, float* rew, float* starts,
@@ -194,18 +239,7 @@ extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* la
     A.eps = eps; A.seed = seed; A.noise_offset = noise_offset; A.env_offset = env_offset;
     A.gamma = (float)gamma;
     A.ep_r = ep_r; A.ep_l = ep_l; A.ep_count = ep_count; A.ring_cap = ring_cap;
-    const size_t smem = (smem_w_floats(A.O) + RO_WARPS * (MAX_OBS * RO_E + 128 * RO_E)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA(cudaFuncSetAttribute(point_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     100 * 1024));
-        attr_set = true;
-    }
-    const int64_t warps = (env->n + RO_E - 1) / RO_E;
-    const int blocks = (int)((warps + RO_WARPS - 1) / RO_WARPS);
-    point_rollout_kernel<<<blocks, RO_WARPS * 32, smem, (cudaStream_t)stream>>>(A);
-    MR_CHECK_LAUNCH();
-    return MR_OK;
+    return launch_rollout(A, env->n, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
