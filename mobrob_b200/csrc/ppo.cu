@@ -39,6 +39,7 @@ struct GradArgs {
     const float* adv;       // [T][N]
     const float* ret;       // [T][N]
     const int64_t* perm;    // [mb_size] env-major sample ids (n * T + t)
+    const int32_t* rows;    // tensor-core kernels: the same samples as time-major buffer rows (t * N + n)
     int64_t mb_size;
     const double* mb_stats; // (sum adv, sum adv^2, count) of the GLOBAL minibatch
     int64_t N, T;
@@ -641,6 +642,17 @@ adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm
     }
 }
 
+// env-major sample ids (RolloutBuffer.swap_and_flatten order, n * T + t) -> rows of the time-major
+// buffers (t * N + n), once per epoch, so that the gather in the tensor-core kernels needs no division
+__global__ void __launch_bounds__(256) perm_to_rows_kernel(const int64_t* __restrict__ perm, int64_t n_samples,
+                                                           int64_t N, int64_t T, int32_t* __restrict__ rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    const unsigned id = (unsigned)perm[i];
+    const unsigned n = id / (unsigned)T, t = id - n * (unsigned)T;
+    rows[i] = (int32_t)((int64_t)t * N + n);
+}
+
 // Device-side index stream for RolloutBuffer.get when the permutation need not come from the host:
 // out[i] = P(i), P a keyed bijection of [0, n) -- four rounds of (odd multiply, xor-shift, add key)
 // on the enclosing power-of-two domain, cycle-walked back into range.  One thread per index, no
@@ -725,7 +737,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 
 template <int O_PAD>
 __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, int O) {
-    static_assert(PG_THREADS == tc::THREADS, "both gradient paths use 256 threads");
     constexpr bool TC = false;   // fp32 CUDA-core cross-check path; the product path is ppo_epoch_tc_kernel
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_grp[PG_THREADS];
@@ -1104,6 +1115,22 @@ static bool use_tc() {
     return v == 1;
 }
 
+// library-owned scratch (one per device): the epoch's samples as buffer rows, for the tensor-core kernels
+static int rows_scratch(int dev, int64_t n, int32_t** out) {
+    static int32_t* buf[16] = {nullptr};
+    static int64_t cap[16] = {0};
+    MR_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
+    if (cap[dev] < n) {
+        if (buf[dev]) MR_CUDA(cudaFree(buf[dev]));
+        buf[dev] = nullptr;
+        cap[dev] = 0;
+        MR_CUDA(cudaMalloc(&buf[dev], (size_t)n * sizeof(int32_t)));
+        cap[dev] = n;
+    }
+    *out = buf[dev];
+    return MR_OK;
+}
+
 static size_t grad_smem_bytes(int O, int O_PAD) {
     size_t f = smem_w_floats(O) + 8192 + (size_t)O_PAD * PG_SP + 3 * 128 * PG_SP + PG_S * 4 +
                PG_WARPS * 32 * 16;
@@ -1165,7 +1192,7 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
                "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     MR_REQUIRE(mb_size > 0, "empty minibatch");
-    GradArgs A{params, obs, act, old_logp, adv, ret, perm, mb_size, mb_stats, N, T,
+    GradArgs A{params, obs, act, old_logp, adv, ret, perm, nullptr, mb_size, mb_stats, N, T,
                clip_range, ent_coef, vf_coef, normalize_adv, partials};
     const int o_pad = obs_dim <= 16 ? 16 : 32;
     const size_t smem = grad_smem_bytes(obs_dim, o_pad);
@@ -1183,6 +1210,15 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
     int grid;
     if (use_tc()) {
         MR_REQUIRE(obs_dim < 32 && max_parts >= 2, "tensor-core path needs obs_dim < 32");
+        MR_REQUIRE(N * T < (int64_t(1) << 31), "tensor-core path indexes samples with 32 bits");
+        int dev = 0;
+        MR_CUDA(cudaGetDevice(&dev));
+        int32_t* rows = nullptr;
+        int rc = rows_scratch(dev, mb_size, &rows);
+        if (rc != MR_OK) return rc;
+        perm_to_rows_kernel<<<ceil_div(mb_size, 256), 256, 0, s>>>(perm, mb_size, N, T, rows);
+        MR_CHECK_LAUNCH();
+        A.rows = rows;
         // obs_dim + 1 (bias column) padded to the bf16 MMA K of 16
         const int kp = obs_dim + 1 <= 16 ? 16 : 32;
         const int64_t tiles = (mb_size + tc::TILE - 1) / tc::TILE;
@@ -1340,7 +1376,7 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     const int n_cta = mr_ppo_max_parts();
     MR_REQUIRE(n_cta <= 448, "too many SMs for the scratch layout");
     EpochArgs E;
-    E.G = GradArgs{params, obs, act, old_logp, adv, ret, perm, 0, stats, N, T,
+    E.G = GradArgs{params, obs, act, old_logp, adv, ret, perm, nullptr, 0, stats, N, T,
                    clip_range, ent_coef, vf_coef, normalize_adv, partials};
     E.n_samples = n_samples; E.batch = batch_size; E.stats = stats; E.rank_share = rank_share;
     E.params = params; E.exp_avg = exp_avg; E.exp_avg_sq = exp_avg_sq; E.step = step;
@@ -1374,7 +1410,14 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
         attr_set = true;
     }
     if (tcp) {
-        MR_REQUIRE(n_samples < (int64_t(1) << 31), "tensor-core path indexes samples with 32 bits");
+        MR_REQUIRE(n_samples < (int64_t(1) << 31) && N * T < (int64_t(1) << 31),
+                   "tensor-core path indexes samples with 32 bits");
+        int32_t* rows = nullptr;
+        int rc = rows_scratch(dev, n_samples, &rows);
+        if (rc != MR_OK) return rc;
+        perm_to_rows_kernel<<<ceil_div(n_samples, 256), 256, 0, s>>>(perm, n_samples, N, T, rows);
+        MR_CHECK_LAUNCH();
+        E.G.rows = rows;
         const int stride = grad_stride(obs_dim);
         MR_REQUIRE((((stride + n_cta - 1) / n_cta + 3) >> 2) <= 32, "gradient slice per CTA too wide");
     }
@@ -1382,7 +1425,7 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     void* args[] = {&E, &O};
     const void* fn = tcp ? (o_pad == 16 ? (const void*)ppo_epoch_tc_kernel<16> : (const void*)ppo_epoch_tc_kernel<32>)
                          : (o_pad == 16 ? (const void*)ppo_epoch_kernel<16> : (const void*)ppo_epoch_kernel<32>);
-    MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(PG_THREADS), args, smem, s));
+    MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(tcp ? tc::THREADS : PG_THREADS), args, smem, s));
     mr::count_launch();
     return MR_OK;
 }
