@@ -167,7 +167,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -301,7 +301,7 @@ def run_ours(args):
             "roofline": roofline, "roofline_env_step": env_roof}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -397,7 +397,27 @@ def cpu_baseline(args):
             "reference_stack_historical": "1026 env-steps/s (SB3 + mujoco-py, 2 subproc envs; BASELINE.md)"}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: keep a private handle to the real stdout and point
+    fd 1 at stderr, so that anything a library prints (NCCL's version banner, torch warnings)
+    cannot land in front of it."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    _claim_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -335,6 +335,7 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
     e->device = device;
     e->cfg.time_limit = time_limit;
     e->cfg.terminate_on_goal = terminate_on_goal ? 1 : 0;
+    e->cfg.pk = point::make_k();
     size_t bytes = kind == MR_ENV_POINT ? PointState::slab_bytes(n_envs) : CarSoA::slab_bytes(n_envs);
     cudaError_t err = cudaMalloc(&e->slab, bytes);
     if (err != cudaSuccess) {

@@ -13,6 +13,7 @@ namespace mr {
 struct EnvCfg {
     int time_limit;         // <= 0: no TimeLimit wrapper
     int terminate_on_goal;  // EnvWrapper(terminate_on_goal=...)
+    point::K pk;            // integrator constants of the point robot (constant-bank operands)
 };
 
 // Arrays touched only by resets (and by the reference-view export).
@@ -93,7 +94,7 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
     const double prevx = h.d.px, prevy = h.d.py;  // _prev_pos == position before the step
     double hc, hs;  // cos / sin of the heading after the step
-    point::substeps(h.d, (double)h.cx, (double)h.cz, hc, hs);
+    point::substeps(cfg.pk, h.d, (double)h.cx, (double)h.cz, hc, hs);
     const double gx = (double)h.gx, gy = (double)h.gy;
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.d.px, h.d.py);
@@ -109,7 +110,7 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
-    point::sensors_cs(h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
+    point::sensors_cs(cfg.pk, h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
     if (r.done) {
 #pragma unroll
         for (int k = 0; k < point::OBS; ++k) term_obs[k] = obs[k];

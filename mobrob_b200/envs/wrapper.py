@@ -154,9 +154,11 @@ class MujocoGoalEnv(EnvWrapper, ABC):
     def _write_state(self, s):
         self.env.set_state(torch.as_tensor(s[None]))
 
+    GOAL_SLOT = 11  # index of the goal (x, y) in the reference-view state vector
+
     def _set_goal(self, goal):
         s = self._state()
-        s[11:13] = np.asarray(goal, dtype=np.float32)[:2]
+        s[self.GOAL_SLOT:self.GOAL_SLOT + 2] = np.asarray(goal, dtype=np.float32)[:2]
         self._write_state(s)
 
     def get_pos(self) -> np.ndarray:
@@ -209,13 +211,40 @@ def get_env(env_name: str, enable_gui: bool = False, terminate_on_goal: bool = F
             time_limit: int | None = None):
     if env_name == "point":
         env = PointEnv(enable_gui, terminate_on_goal)
-    elif env_name in ("car", "doggo", "drone", "turtlebot3"):
-        raise NotImplementedError(f"{env_name}: not built on the B200 path yet (see DESIGN.md scope)")
+    elif env_name == "car":
+        env = CarEnv(enable_gui, terminate_on_goal)
+    elif env_name in ("doggo", "drone", "turtlebot3"):
+        raise NotImplementedError(f"{env_name}: outside the scope of the B200 path (SURVEY.md section 2)")
     else:
         raise ValueError(f"Env {env_name} not found")
     if time_limit is not None:
         env = TimeLimit(env, max_episode_steps=time_limit)
     return env
+
+
+class CarEnv(MujocoGoalEnv):
+    """CarEnv (wrapper.py:308-326): free-joint root; set_pos only rewrites qpos[0:2]."""
+    ENV_NAME = "car"
+    render_mode = "rgb_array"
+    GOAL_SLOT = 26  # qpos(13) qvel(11) ctrl(2) goal(2) elapsed ep_ret
+
+    def _engine_reset(self):
+        # Engine.reset(): new MjSim -- default pose at the origin, body z from car.xml:12, heading
+        # drawn from RandomState(_seed), zero velocities and ctrl (engine.py:1000-1021, world.py:52-54)
+        self._engine_seed += 1
+        heading = _engine_heading(self._engine_seed)
+        s = self._state()
+        s[0:24] = 0.0
+        s[2] = 0.1
+        s[3], s[6] = np.cos(0.5 * heading), np.sin(0.5 * heading)
+        s[9] = 1.0            # ball joint quaternion
+        s[24:26] = 0.0        # data.ctrl
+        self._write_state(s)
+
+    def set_pos(self, pos):
+        s = self._state()
+        s[0:2] = np.asarray(pos, dtype=np.float64)[:2]
+        self._write_state(s)
 
 
 class TimeLimit:
