@@ -310,7 +310,7 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 
 # dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
-EPOCH_KERNEL_DRAM_BYTES = 162.2e6
+EPOCH_KERNEL_DRAM_BYTES = 151.8e6  # 144.7 MB read + 7.1 MB written (profiles/r01_ncu_full_final.txt)
 
 
 def time_epoch_kernel(model, dev):
