@@ -44,12 +44,12 @@ point_step_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act,
     const int64_t block_start = (int64_t)blockIdx.x * STEP_THREADS;
     const int64_t i = block_start + threadIdx.x;
     if (i < st.n) {
-        PointHot h = st.load(i);
+        PointHot h = st.load_step(i);
         float2 a = act[i];
         float tobs[point::OBS];
         StepResult r = point_env_step(h, st.cold, i, a.x, a.y, cfg,
                                       &s_obs[threadIdx.x * OBS_PAD], tobs);
-        st.store(i, h);
+        st.store_step(i, h, r.done);
         rew[i] = r.rew;
         done[i] = r.done ? 1 : 0;
         trunc[i] = r.trunc ? 1 : 0;

@@ -110,7 +110,7 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
-    point::sensors_cs(cfg.pk, h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
+    point::sensors_cs(cfg.pk, h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs, dcur);
     if (r.done) {
 #pragma unroll
         for (int k = 0; k < point::OBS; ++k) term_obs[k] = obs[k];

@@ -46,66 +46,111 @@ struct Dyn {
 __device__ __forceinline__ double clampd(double x, double lo, double hi) {
     return fmin(fmax(x, lo), hi);
 }
+// clamp to [-lim, lim]: one compare on |x| and a select (fmin / fmax on fp64 carry NaN-propagation
+// code: 18 instructions per clamp in the substep loop, profiles/r01 SASS)
+__device__ __forceinline__ double clamp_sym(double x, double lim) {
+    return fabs(x) > lim ? copysign(lim, x) : x;
+}
 
 // Numeric constants of the integrator.  They travel as KERNEL PARAMETERS (inside EnvCfg): a fp64
 // literal costs two uniform-register moves every time it is used (profiles/: 36 % of the env-step
 // kernel's instructions were UMOV / IMAD.MOV), a parameter is a constant-bank operand of the DFMA.
+//
+// The solve (M + h D)^-1 (Q_act - D qdot - C) is the Schur complement on the hinge; because
+// B^2 + C^2 = (mc)^2 is constant both pivots are constants, and with c, s = cos / sin of the
+// heading the coupling term c r1 - s r0 collapses to -d_slide u2 (u2 = c vy - s vx, the lateral
+// body velocity): the angular acceleration is LINEAR in (servo error e, omega, u2),
+//     alpha = al_e e + al_w omega + al_u u2,
+// and the linear accelerations follow as a = (r + mc (s, -c) alpha) / A.
 struct K {
-    double mc, d_slide, d_hinge, gear, flim, h;
-    double inv_a[2], inv_schur[2], mc_a[2];   // [0] plain M (mj_forward), [1] M + h D (mj_step)
-    double s3, s5, s7, c2, c4, c6, c8;        // Taylor coefficients of sin / cos
+    double mc, d_slide, gear, flim, h;
+    double al_e[2], al_w[2], al_u[2];         // [0] plain M (mj_forward), [1] M + h D (mj_step)
+    double inv_a0;                            // 1 / m of mj_forward
+    double h_inv_a, kd, h_mc_a;               // implicit solve: h / A, 1 - h d / A, h mc / A
+    double rot_max;                           // largest |h omega| the Taylor rotation accepts
+    double s3, s5, c2, c4, c6;                // Taylor coefficients of sin / cos (small angle)
+    double two_over_pi, pio2_hi, pio2_lo, trig_max;
+    double ks[6], kc[6];                      // sin / cos kernels on [-pi/4, pi/4]
 };
 __host__ __device__ inline K make_k() {
     K k;
-    k.mc = MC; k.d_slide = D_SLIDE; k.d_hinge = D_HINGE; k.gear = GEAR; k.flim = FLIM; k.h = H;
+    k.mc = MC; k.d_slide = D_SLIDE; k.gear = GEAR; k.flim = FLIM; k.h = H;
     for (int i = 0; i < 2; ++i) {
         const double h = i ? H : 0.0;
         const double A = MASS + h * D_SLIDE;
         const double DTH = I_O + h * D_HINGE;
         const double SCHUR = DTH - MC * MC / A;
-        k.inv_a[i] = 1.0 / A;
-        k.inv_schur[i] = 1.0 / SCHUR;
-        k.mc_a[i] = MC / A;
+        k.al_e[i] = GEAR / SCHUR;
+        k.al_w[i] = -D_HINGE / SCHUR;
+        k.al_u[i] = (MC / A) * D_SLIDE / SCHUR;
     }
-    k.s3 = -1.0 / 6.0; k.s5 = 1.0 / 120.0; k.s7 = -1.0 / 5040.0;
-    k.c2 = -0.5; k.c4 = 1.0 / 24.0; k.c6 = -1.0 / 720.0; k.c8 = 1.0 / 40320.0;
+    k.inv_a0 = 1.0 / MASS;
+    k.h_inv_a = H / (MASS + H * D_SLIDE);
+    k.kd = 1.0 - k.h_inv_a * D_SLIDE;
+    k.h_mc_a = k.h_inv_a * MC;
+    k.rot_max = 0.0125;
+    k.s3 = -1.0 / 6.0; k.s5 = 1.0 / 120.0;
+    k.c2 = -0.5; k.c4 = 1.0 / 24.0; k.c6 = -1.0 / 720.0;
+    k.two_over_pi = 0.63661977236758134308;
+    k.pio2_hi = 1.5707963267948966;      // double(pi / 2)
+    k.pio2_lo = 6.123233995736766e-17;   // pi / 2 - double(pi / 2)
+    k.trig_max = 1.0e5;
+    const double ks[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                          2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+    const double kc[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                          -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+    for (int i = 0; i < 6; ++i) { k.ks[i] = ks[i]; k.kc[i] = kc[i]; }
     return k;
 }
 
-// (M + h D)^-1 (Q_act - D qdot - C) by the Schur complement on the hinge (B^2 + C^2 = (mc)^2
-// is constant, so both pivots -- and their reciprocals -- are constants: the solve is
-// multiplications only).  c, s = cos/sin of the heading.
-template <bool IMPLICIT>
-__device__ __forceinline__ void accel(const K& k, double c, double s, double vx, double vy, double om,
-                                      double f, double cz, double& ax, double& ay, double& al) {
-    constexpr int I = IMPLICIT ? 1 : 0;
-    double tau = k.gear * clampd(cz - k.gear * om, -k.flim, k.flim);  // velocity servo, kv = 1
-    double w2 = om * om;
-    double r0 = f * c - k.d_slide * vx + k.mc * c * w2;
-    double r1 = f * s - k.d_slide * vy + k.mc * s * w2;
-    double r2 = tau - k.d_hinge * om;
-    double t = k.mc_a[I] * (c * r1 - s * r0);
-    al = (r2 - t) * k.inv_schur[I];
-    ax = (r0 + k.mc * s * al) * k.inv_a[I];
-    ay = (r1 - k.mc * c * al) * k.inv_a[I];
-}
-
-// (c, s) <- rotation of (c, s) by the small angle a: Taylor series of sin / cos (|a| < 0.02 ->
-// truncation below 1e-18), so the heading's sine / cosine follow the integrator without a
-// trigonometric call per substep.  Large steps (never reached: |omega| stays below ~4 rad/s) fall
-// back to the exact evaluation at the new heading.
 static __device__ __noinline__ double2 sincos_cold(double psi) {   // (cos, sin), by value: no stack slot
     double s, c;
     sincos(psi, &s, &c);
     return make_double2(c, s);
 }
-__device__ __forceinline__ void rotate_cs(const K& k, double& c, double& s, double a, double psi_new) {
-    if (fabs(a) < 0.02) {
+
+// sin / cos of the heading at the start of an env step: two-constant Cody-Waite reduction (exact
+// products inside the FMAs) and the classical minimax kernels on [-pi/4, pi/4], every coefficient a
+// constant-bank operand.  <= 1 ulp for |x| < 1e5 (checked against libm); beyond that the library
+// routine (Payne-Hanek) runs out of line.  The library call inlined here cost ~85 instructions,
+// half of them moves of its fp64 literals.
+__device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double& c) {
+    if (fabs(x) < k.trig_max) {
+        const double kq = rint(x * k.two_over_pi);
+        const int q = (int)kq;
+        double r = fma(-kq, k.pio2_hi, x);
+        r = fma(-kq, k.pio2_lo, r);
+        const double z = r * r;
+        double ps = fma(z, k.ks[5], k.ks[4]);
+        double pc = fma(z, k.kc[5], k.kc[4]);
+        ps = fma(z, ps, k.ks[3]); pc = fma(z, pc, k.kc[3]);
+        ps = fma(z, ps, k.ks[2]); pc = fma(z, pc, k.kc[2]);
+        ps = fma(z, ps, k.ks[1]); pc = fma(z, pc, k.kc[1]);
+        ps = fma(z, ps, k.ks[0]); pc = fma(z, pc, k.kc[0]);
+        const double sr = fma(r * z, ps, r);
+        const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+        const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+        s = (q & 2) ? -a : a;
+        c = ((q + 1) & 2) ? -b : b;
+    } else {
+        const double2 cs = sincos_cold(x);
+        c = cs.x;
+        s = cs.y;
+    }
+}
+
+// (c, s) <- rotation of (c, s) by the small angle a: Taylor series of sin / cos (|a| < 0.0125 ->
+// truncation below 1e-17), so the heading's sine / cosine follow the integrator without a
+// trigonometric call per substep.  Large steps (never reached: |omega| stays below ~4 rad/s, i.e.
+// |a| < 0.008) fall back to the exact evaluation at the new heading.
+__device__ __forceinline__ void rotate_cs(const K& k, double s3, double c4, double& c, double& s, double a,
+                                          double psi_new) {
+    if (fabs(a) < k.rot_max) {
         const double x = a * a;
-        const double sd = a * (1.0 + x * (k.s3 + x * (k.s5 + x * k.s7)));
-        const double cd = 1.0 + x * (k.c2 + x * (k.c4 + x * (k.c6 + x * k.c8)));
+        const double sd = a * fma(x, fma(x, k.s5, s3), 1.0);
+        const double cd = fma(x, fma(x, fma(x, k.c6, c4), k.c2), 1.0);
         const double c2 = c * cd - s * sd;
-        s = s * cd + c * sd;
+        s = fma(s, cd, c * sd);
         c = c2;
     } else {
         const double2 cs = sincos_cold(psi_new);   // out of line: keeps the substep loop free of its constants
@@ -114,23 +159,37 @@ __device__ __forceinline__ void rotate_cs(const K& k, double& c, double& s, doub
     }
 }
 
+// opaque copy: pins a loop-invariant constant in a register (the compiler otherwise re-loads it from
+// the constant bank inside the substep loop whenever an FMA needs two constants)
+__device__ __forceinline__ double pin(double x) {
+    asm volatile("" : "+d"(x));
+    return x;
+}
+
 // Engine.step physics: ctrl already clipped to [-1, 1].  Returns cos / sin of the final heading
-// (one exact sincos at the start of the env step, ten incremental rotations).
+// (one sincos at the start of the env step, ten incremental rotations).  With u2 = c vy - s vx,
+//     alpha = al_e e + al_w omega + al_u u2            (servo error e clamped to +-flim)
+//     v    <- (1 - h d / A) v + (h / A)(f + mc omega^2) (c, s) + (h mc / A) alpha (s, -c)
+// 33 fp64 operations per substep.
 __device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx, double cz, double& c, double& s) {
-    const double f = k.gear * clampd(cx, -k.flim, k.flim);  // site motor along body x
-    sincos(d.psi, &s, &c);
-#pragma unroll 1
+    const double fh = k.h_inv_a * (k.gear * clamp_sym(cx, k.flim));  // site motor along body x, times h / A
+    const double flim = pin(k.flim), s3 = pin(k.s3), c4 = pin(k.c4);
+    sincos_k(k, d.psi, s, c);
+#pragma unroll 2
     for (int i = 0; i < FRAME_SKIP; ++i) {
-        double ax, ay, al;
-        accel<true>(k, c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
-        d.vx += k.h * ax;
-        d.vy += k.h * ay;
-        d.om += k.h * al;
-        d.px += k.h * d.vx;
-        d.py += k.h * d.vy;
+        const double e = clamp_sym(fma(-k.gear, d.om, cz), flim);  // velocity servo, kv = 1
+        const double qh = fma(k.h_mc_a, d.om * d.om, fh);           // thrust + centripetal term, along body x
+        const double u2 = fma(-s, d.vx, c * d.vy);
+        const double al = fma(k.al_u[1], u2, fma(k.al_w[1], d.om, k.al_e[1] * e));
+        const double mah = k.h_mc_a * al;
+        d.vx = fma(mah, s, fma(qh, c, k.kd * d.vx));
+        d.vy = fma(-mah, c, fma(qh, s, k.kd * d.vy));
+        d.om = fma(k.h, al, d.om);
+        d.px = fma(k.h, d.vx, d.px);
+        d.py = fma(k.h, d.vy, d.py);
         const double a = k.h * d.om;
         d.psi += a;
-        rotate_cs(k, c, s, a, d.psi);
+        rotate_cs(k, s3, c4, c, s, a, d.psi);
     }
 }
 __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
@@ -139,20 +198,26 @@ __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
     substeps(k, d, cx, cz, c, s);
 }
 
-// Engine.obs(): mj_forward at the current state with the current ctrl; sorted-key layout
+// Engine.obs(): mj_forward at the current state with the current ctrl (plain M^-1); sorted-key layout
 // [accelerometer 0:3 | goal_compass 3:5 | gyro 5:8 | magnetometer 8:11 | velocimeter 11:14].
-// c, s = cos / sin of d.psi.
+// c, s = cos / sin of d.psi.  Everything is evaluated in the body frame: with
+// u = R^T v the accelerometer is a1 = (q - d u1) / m, a2 = -(d u2 + mc alpha) / m.
+// goal_norm: ||goal - pos|| (the reference divides by the norm of the ROTATED vector, equal to it up
+// to rounding far below float32; the env step has it already for the reward).
 __device__ __forceinline__ void sensors_cs(const K& k, const Dyn& d, double c, double s, double cx, double cz,
-                                           float gx, float gy, float* o) {
-    const double f = k.gear * clampd(cx, -k.flim, k.flim);
-    double ax, ay, al;
-    accel<false>(k, c, s, d.vx, d.vy, d.om, f, cz, ax, ay, al);
-    o[0] = (float)(c * ax + s * ay);
-    o[1] = (float)(-s * ax + c * ay);
+                                           float gx, float gy, float* o, double goal_norm) {
+    const double f = k.gear * clamp_sym(cx, k.flim);
+    const double e = clamp_sym(fma(-k.gear, d.om, cz), k.flim);
+    const double u1 = fma(s, d.vy, c * d.vx);
+    const double u2 = fma(-s, d.vx, c * d.vy);
+    const double q = fma(k.mc, d.om * d.om, f);
+    const double al = fma(k.al_u[0], u2, fma(k.al_w[0], d.om, k.al_e[0] * e));
+    o[0] = (float)(fma(-k.d_slide, u1, q) * k.inv_a0);
+    o[1] = (float)(-fma(k.d_slide, u2, k.mc * al) * k.inv_a0);
     o[2] = (float)GRAV;
-    double dx = (double)gx - d.px, dy = (double)gy - d.py;
-    double ex = c * dx + s * dy, ey = -s * dx + c * dy;
-    double inv = 1.0 / (sqrt(ex * ex + ey * ey) + 0.001);
+    const double dx = (double)gx - d.px, dy = (double)gy - d.py;
+    const double ex = fma(s, dy, c * dx), ey = fma(-s, dx, c * dy);
+    const double inv = 1.0 / (goal_norm + 0.001);
     o[3] = (float)(ex * inv);
     o[4] = (float)(ey * inv);
     o[5] = 0.f;
@@ -161,8 +226,8 @@ __device__ __forceinline__ void sensors_cs(const K& k, const Dyn& d, double c, d
     o[8] = (float)(s * MAG_Y);
     o[9] = (float)(c * MAG_Y);
     o[10] = 0.f;
-    o[11] = (float)(c * d.vx + s * d.vy);
-    o[12] = (float)(-s * d.vx + c * d.vy);
+    o[11] = (float)u1;
+    o[12] = (float)u2;
     o[13] = 0.f;
 }
 __device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
@@ -170,7 +235,8 @@ __device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, floa
     double s, c;
     sincos(d.psi, &s, &c);
     const K k = make_k();
-    sensors_cs(k, d, c, s, cx, cz, gx, gy, o);
+    const double dx = (double)gx - d.px, dy = (double)gy - d.py;
+    sensors_cs(k, d, c, s, cx, cz, gx, gy, o, sqrt(dx * dx + dy * dy));
 }
 
 // ||a - b|| exactly as numpy evaluates it on two-vectors (no contraction): the reached flag
