@@ -377,7 +377,7 @@ def time_env_step_kernel(dev, peaks):
     return {"kernel": "point_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
             "n_envs": n, "env_steps_per_s": n / (ms * 1e-3),
-            "note": "algorithmic 145 B/env-step (SURVEY 8d); state is fp64 so physical traffic is ~205 B"}
+            "note": "algorithmic 145 B/env-step (SURVEY 8d); the state is fp64, physical traffic is 198 B/env-step (76 read, 122 written)"}
 
 
 def cpu_baseline(args):

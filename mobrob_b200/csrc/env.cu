@@ -22,33 +22,62 @@ void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 // ---------------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 128;
-constexpr int OBS_PAD = point::OBS + 1;  // 15-float rows: conflict-free thread-per-row writes
-
+// Observation rows leave the block as one contiguous span of rows * OBS floats.  Each thread puts
+// its row into shared memory as 7 float2 (dense 56-byte rows: a half-warp's 8-byte stores cover
+// all 32 banks once), then the block streams the span out as float4 -- 4 load/store pairs per
+// thread instead of 14 scalar ones with an index division each (that loop was 18 % of the
+// env-step kernel's instructions, profiles/r01_env_step).
+__device__ __forceinline__ void stage_row(float* smem, const float (&o)[point::OBS]) {
+    float2* row = reinterpret_cast<float2*>(smem + threadIdx.x * point::OBS);
+#pragma unroll
+    for (int j = 0; j < point::OBS / 2; ++j) row[j] = make_float2(o[2 * j], o[2 * j + 1]);
+}
 __device__ __forceinline__ void store_rows_coalesced(float* __restrict__ dst, const float* smem,
-                                                     int64_t block_start, int rows, int64_t n) {
-    // dst rows [block_start, block_start + rows) are one contiguous span of rows * OBS floats
+                                                     int64_t block_start, int rows) {
     const int total = rows * point::OBS;
-    float* base = dst + block_start * point::OBS;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int r = idx / point::OBS, k = idx - r * point::OBS;
-        base[idx] = smem[r * OBS_PAD + k];
+    float* base = dst + block_start * point::OBS;   // block_start * 56 B is a multiple of 16
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int nvec = total >> 2;
+        const float4* src4 = reinterpret_cast<const float4*>(smem);
+        float4* dst4 = reinterpret_cast<float4*>(base);
+#pragma unroll
+        for (int v = 0; v < (STEP_THREADS * point::OBS / 4 + STEP_THREADS - 1) / STEP_THREADS; ++v) {
+            const int idx = threadIdx.x + v * STEP_THREADS;
+            if (idx < nvec) dst4[idx] = src4[idx];
+        }
+        const int idx = (nvec << 2) + threadIdx.x;
+        if (idx < total) base[idx] = smem[idx];
+    } else {
+        for (int idx = threadIdx.x; idx < total; idx += STEP_THREADS) base[idx] = smem[idx];
     }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(STEP_THREADS, MINB)
 point_step_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act,
                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
                   uint8_t* __restrict__ trunc, float* __restrict__ term_obs,
-                  double* __restrict__ ep_ret, int32_t* __restrict__ ep_len) {
-    __shared__ float s_obs[STEP_THREADS * OBS_PAD];
-    const int64_t block_start = (int64_t)blockIdx.x * STEP_THREADS;
+                  double* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int64_t pf_dist) {
+    __shared__ __align__(16) float s_obs[STEP_THREADS * point::OBS];
+    // pf_dist < 0: this launch walks the envs downwards.  Consecutive steps alternate, so the state a
+    // step wrote last -- still dirty in the 126 MB L2 -- is what the next step reads (and overwrites)
+    // first: those lines never travel to HBM in between.
+    const int64_t block = pf_dist < 0 ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
+    const int64_t block_start = block * STEP_THREADS;
     const int64_t i = block_start + threadIdx.x;
+    if (pf_dist > 1 || pf_dist < -1) {
+        const int64_t bp = block + pf_dist / STEP_THREADS;   // the block that starts one wave later
+        if (bp >= 0 && bp < (int64_t)gridDim.x) {
+            st.prefetch_tile(bp, threadIdx.x);
+            if (threadIdx.x >= 120) asm volatile("prefetch.global.L2 [%0];" ::"l"(act + bp * STEP_THREADS + (threadIdx.x - 120) * 16));
+        }
+    }
     if (i < st.n) {
         PointHot h = st.load_step(i);
         float2 a = act[i];
-        float tobs[point::OBS];
-        StepResult r = point_env_step(h, st.cold, i, a.x, a.y, cfg,
-                                      &s_obs[threadIdx.x * OBS_PAD], tobs);
+        float o[point::OBS], tobs[point::OBS];
+        StepResult r = point_env_step(h, st.cold, i, a.x, a.y, cfg, o, tobs);
+        stage_row(s_obs, o);
         st.store_step(i, h, r.done);
         rew[i] = r.rew;
         done[i] = r.done ? 1 : 0;
@@ -64,7 +93,7 @@ point_step_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act,
     }
     __syncthreads();
     int rows = (int)min((int64_t)STEP_THREADS, st.n - block_start);
-    store_rows_coalesced(obs, s_obs, block_start, rows, st.n);
+    store_rows_coalesced(obs, s_obs, block_start, rows);
 }
 
 __global__ void __launch_bounds__(STEP_THREADS)
@@ -87,17 +116,18 @@ point_reset_kernel(PointState st, const uint8_t* __restrict__ mask, int first,
 
 __global__ void __launch_bounds__(STEP_THREADS)
 point_obs_kernel(PointState st, float* __restrict__ obs) {
-    __shared__ float s_obs[STEP_THREADS * OBS_PAD];
+    __shared__ __align__(16) float s_obs[STEP_THREADS * point::OBS];
     const int64_t block_start = (int64_t)blockIdx.x * STEP_THREADS;
     const int64_t i = block_start + threadIdx.x;
     if (i < st.n) {
         PointHot h = st.load(i);
-        point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy,
-                       &s_obs[threadIdx.x * OBS_PAD]);
+        float o[point::OBS];
+        point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy, o);
+        stage_row(s_obs, o);
     }
     __syncthreads();
     int rows = (int)min((int64_t)STEP_THREADS, st.n - block_start);
-    store_rows_coalesced(obs, s_obs, block_start, rows, st.n);
+    store_rows_coalesced(obs, s_obs, block_start, rows);
 }
 
 // reference view: qpos(3) qvel(3) body_xy(2) psi0(1) ctrl(2) goal(2) elapsed(1) ep_ret(1)
@@ -144,8 +174,9 @@ __global__ void point_set_state_kernel(PointState st, const double* __restrict__
 __global__ void point_get_pos_kernel(PointState st, double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.n) return;
-    out[2 * i] = st.px[i];
-    out[2 * i + 1] = st.py[i];
+    const double2 p = st.pos(i);
+    out[2 * i] = p.x;
+    out[2 * i + 1] = p.y;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -406,10 +437,21 @@ int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* 
                 uint8_t* trunc, float* term_obs, double* ep_ret, int32_t* ep_len, void* stream) {
     MR_REQUIRE(env && act && obs && rew && done && trunc, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (env->kind == MR_ENV_POINT)
-        point_step_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(
-            env->point, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs, ep_ret, ep_len);
-    else
+    if (env->kind == MR_ENV_POINT) {
+        // tuning knobs (measured on B200 at 4M envs, profiles/r01_env_step_sweep.txt): 5 blocks per SM
+        // (96 registers, no spills) and a prefetch distance of 4 blocks per SM are the defaults
+        static const int minb = getenv("MR_STEP_MINB") ? atoi(getenv("MR_STEP_MINB")) : 5;
+        auto kern = minb == 8 ? point_step_kernel<8> : minb == 7 ? point_step_kernel<7> : minb == 6 ? point_step_kernel<6>
+                    : minb == 4 ? point_step_kernel<4> : point_step_kernel<5>;
+        static const int pf_blocks = getenv("MR_STEP_PF") ? atoi(getenv("MR_STEP_PF")) : 592;
+        static const int flip = getenv("MR_STEP_FLIP") ? atoi(getenv("MR_STEP_FLIP")) : 1;
+        const int64_t dist = pf_blocks > 0 ? (int64_t)pf_blocks * STEP_THREADS : 1;
+        const bool down = flip && env->step_flip;
+        env->step_flip ^= 1;
+        kern<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(
+            env->point, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs, ep_ret, ep_len,
+            down ? -dist : dist);
+    } else
         car_step_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(
             env->car, env->carK, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs,
             ep_ret, ep_len);

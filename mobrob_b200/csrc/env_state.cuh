@@ -1,6 +1,13 @@
-// HBM layout of the batched environment state: one slab per mr_env, struct-of-arrays,
-// every array 256-byte aligned, env index fastest so a warp's loads are 128/256-byte
-// coalesced.  "Hot" arrays are read+written by every step; "cold" arrays only by resets.
+// HBM layout of the batched environment state: one slab per mr_env, every array 256-byte aligned.
+// "Hot" fields are read+written by every step; "cold" arrays only by resets.
+//
+// Hot state is TILED: a tile holds the hot fields of 128 consecutive envs (= one block of the
+// env-step kernel), field-major inside the tile, 9728 contiguous bytes:
+//     px py psi vx vy om ep_ret  (f64, 1024 B each) | ctrl goal (float2, 1024 B each) | elapsed (i32, 512 B)
+// A warp's loads stay 128/256-byte coalesced, every field of an env sits at a COMPILE-TIME offset
+// from one per-thread address (a plain struct-of-arrays spent 8 % of the env-step kernel's
+// instructions on 64-bit address arithmetic for its 10 arrays), and the block's whole input is one
+// contiguous range for the L2 prefetch.
 #pragma once
 
 #include "env_car.cuh"
@@ -11,21 +18,18 @@ namespace mr {
 constexpr int POINT_STATE_DIM = 15;
 
 struct PointState {
+    static constexpr int TILE = 128;
+    static constexpr int F_PX = 0, F_PY = 1024, F_PSI = 2048, F_VX = 3072, F_VY = 4096, F_OM = 5120, F_EPRET = 6144,
+                         F_CTRL = 7168, F_GOAL = 8192, F_ELAPSED = 9216, TILE_BYTES = 9728;
     int64_t n;
-    // hot: 6 x f64 + goal float2 + i32 + f64 = 68 B read; + ctrl float2 - goal = 68 B written per env-step
-    double *px, *py, *psi, *vx, *vy, *om;
-    float2* ctrl;
-    float2* goal;
-    int32_t* elapsed;
-    double* ep_ret;
+    char* hot;   // ceil(n / 128) tiles
     EnvCold cold;
 
     static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+    static size_t tiles(int64_t n) { return (size_t)((n + TILE - 1) / TILE); }
     static size_t slab_bytes(int64_t n) {
         size_t b = 0;
-        b += 7 * align_up(n * 8);   // px py psi vx vy om ep_ret
-        b += 2 * align_up(n * 8);   // ctrl goal
-        b += align_up(n * 4);       // elapsed
+        b += align_up(tiles(n) * TILE_BYTES);
         b += 2 * align_up(n * 32);  // pcg_init pcg_goal
         b += align_up(n * 8);       // engine_seed
         b += align_up(n * 8);       // body_xy
@@ -37,11 +41,7 @@ struct PointState {
         n = n_;
         char* p = static_cast<char*>(slab);
         auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
-        px = (double*)take(n * 8); py = (double*)take(n * 8); psi = (double*)take(n * 8);
-        vx = (double*)take(n * 8); vy = (double*)take(n * 8); om = (double*)take(n * 8);
-        ep_ret = (double*)take(n * 8);
-        ctrl = (float2*)take(n * 8); goal = (float2*)take(n * 8);
-        elapsed = (int32_t*)take(n * 4);
+        hot = take(tiles(n) * TILE_BYTES);
         cold.pcg_init = (uint64_t*)take(n * 32); cold.pcg_goal = (uint64_t*)take(n * 32);
         cold.engine_seed = (int64_t*)take(n * 8);
         cold.body_xy = (float2*)take(n * 8);
@@ -49,43 +49,69 @@ struct PointState {
         cold.counts = (int32_t*)take(n * 8);
     }
 
+    // address of env i's 8-byte slot in field 0 of its tile; the other fields are at + F_*
+    __device__ __forceinline__ char* slot(int64_t i) const {
+        return hot + (i >> 7) * TILE_BYTES + ((int)i & (TILE - 1)) * 8;
+    }
+    __device__ __forceinline__ char* tile(int64_t t) const { return hot + t * TILE_BYTES; }
+    template <class T>
+    static __device__ __forceinline__ T& at(char* p, int off) { return *reinterpret_cast<T*>(p + off); }
+    // elapsed is 4 bytes wide: lane * 4 instead of lane * 8
+    static __device__ __forceinline__ int32_t& elapsed_at(char* p, int64_t i) {
+        return *reinterpret_cast<int32_t*>(p + F_ELAPSED - ((int)i & (TILE - 1)) * 4);
+    }
+
     __device__ __forceinline__ PointHot load(int64_t i) const {
+        char* p = slot(i);
         PointHot h;
-        h.d.px = px[i]; h.d.py = py[i]; h.d.psi = psi[i];
-        h.d.vx = vx[i]; h.d.vy = vy[i]; h.d.om = om[i];
-        float2 c = ctrl[i], g = goal[i];
+        h.d.px = at<double>(p, F_PX); h.d.py = at<double>(p, F_PY); h.d.psi = at<double>(p, F_PSI);
+        h.d.vx = at<double>(p, F_VX); h.d.vy = at<double>(p, F_VY); h.d.om = at<double>(p, F_OM);
+        const float2 c = at<float2>(p, F_CTRL), g = at<float2>(p, F_GOAL);
         h.cx = c.x; h.cz = c.y; h.gx = g.x; h.gy = g.y;
-        h.elapsed = elapsed[i];
-        h.ep_ret = ep_ret[i];
+        h.elapsed = elapsed_at(p, i);
+        h.ep_ret = at<double>(p, F_EPRET);
         return h;
     }
+    __device__ __forceinline__ void store(int64_t i, const PointHot& h) const {
+        char* p = slot(i);
+        at<double>(p, F_PX) = h.d.px; at<double>(p, F_PY) = h.d.py; at<double>(p, F_PSI) = h.d.psi;
+        at<double>(p, F_VX) = h.d.vx; at<double>(p, F_VY) = h.d.vy; at<double>(p, F_OM) = h.d.om;
+        at<float2>(p, F_CTRL) = make_float2(h.cx, h.cz);
+        at<float2>(p, F_GOAL) = make_float2(h.gx, h.gy);
+        elapsed_at(p, i) = h.elapsed;
+        at<double>(p, F_EPRET) = h.ep_ret;
+    }
     // env-step variants: data.ctrl is overwritten by the action before anything reads it, and the
-    // goal only changes in a reset -- 8 B less read and 8 B less written per env-step.
+    // goal only changes in a reset -- 8 B less read and 8 B less written per env-step
+    // (68 B read, 68 B written).
     __device__ __forceinline__ PointHot load_step(int64_t i) const {
+        char* p = slot(i);
         PointHot h;
-        h.d.px = px[i]; h.d.py = py[i]; h.d.psi = psi[i];
-        h.d.vx = vx[i]; h.d.vy = vy[i]; h.d.om = om[i];
-        const float2 g = goal[i];
+        h.d.px = at<double>(p, F_PX); h.d.py = at<double>(p, F_PY); h.d.psi = at<double>(p, F_PSI);
+        h.d.vx = at<double>(p, F_VX); h.d.vy = at<double>(p, F_VY); h.d.om = at<double>(p, F_OM);
+        const float2 g = at<float2>(p, F_GOAL);
         h.cx = 0.f; h.cz = 0.f; h.gx = g.x; h.gy = g.y;
-        h.elapsed = elapsed[i];
-        h.ep_ret = ep_ret[i];
+        h.elapsed = elapsed_at(p, i);
+        h.ep_ret = at<double>(p, F_EPRET);
         return h;
     }
     __device__ __forceinline__ void store_step(int64_t i, const PointHot& h, bool was_reset) const {
-        px[i] = h.d.px; py[i] = h.d.py; psi[i] = h.d.psi;
-        vx[i] = h.d.vx; vy[i] = h.d.vy; om[i] = h.d.om;
-        ctrl[i] = make_float2(h.cx, h.cz);
-        if (was_reset) goal[i] = make_float2(h.gx, h.gy);
-        elapsed[i] = h.elapsed;
-        ep_ret[i] = h.ep_ret;
+        char* p = slot(i);
+        at<double>(p, F_PX) = h.d.px; at<double>(p, F_PY) = h.d.py; at<double>(p, F_PSI) = h.d.psi;
+        at<double>(p, F_VX) = h.d.vx; at<double>(p, F_VY) = h.d.vy; at<double>(p, F_OM) = h.d.om;
+        at<float2>(p, F_CTRL) = make_float2(h.cx, h.cz);
+        if (was_reset) at<float2>(p, F_GOAL) = make_float2(h.gx, h.gy);
+        elapsed_at(p, i) = h.elapsed;
+        at<double>(p, F_EPRET) = h.ep_ret;
     }
-    __device__ __forceinline__ void store(int64_t i, const PointHot& h) const {
-        px[i] = h.d.px; py[i] = h.d.py; psi[i] = h.d.psi;
-        vx[i] = h.d.vx; vy[i] = h.d.vy; om[i] = h.d.om;
-        ctrl[i] = make_float2(h.cx, h.cz);
-        goal[i] = make_float2(h.gx, h.gy);
-        elapsed[i] = h.elapsed;
-        ep_ret[i] = h.ep_ret;
+    __device__ __forceinline__ double2 pos(int64_t i) const {
+        char* p = slot(i);
+        return make_double2(at<double>(p, F_PX), at<double>(p, F_PY));
+    }
+    // pull tile t (one block's whole hot input, 76 lines of 128 B) towards L2; called by a block one
+    // wave ahead of the tile's use, thread k takes line k
+    __device__ __forceinline__ void prefetch_tile(int64_t t, int k) const {
+        if (k < TILE_BYTES / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile(t) + k * 128));
     }
 };
 
@@ -102,4 +128,5 @@ struct mr_env {
     mr::CarSoA car;
     mr::car::Consts carK;
     void* scratch = nullptr;  // lazily allocated by mr_rollout_unfused
+    int step_flip = 0;        // env-step kernels alternate the block order (L2 keeps the tail of the last step)
 };

@@ -66,9 +66,11 @@ struct K {
     double mc, d_slide, gear, flim, h;
     double al_e[2], al_w[2], al_u[2];         // [0] plain M (mj_forward), [1] M + h D (mj_step)
     double inv_a0;                            // 1 / m of mj_forward
-    double h_inv_a, kd, h_mc_a;               // implicit solve: h / A, 1 - h d / A, h mc / A
+    double h_inv_a, kd;                       // implicit solve: h / A, 1 - h d / A
+    // substep loop in terms of the heading increment a = h omega (see substep_core)
+    double g_h, q_x, al2_e, al2_w, al2_u, inv_h;
     double rot_max;                           // largest |h omega| the Taylor rotation accepts
-    double s3, s5, c2, c4, c6;                // Taylor coefficients of sin / cos (small angle)
+    double s3, s5, c2, c4, rot_max2;          // Taylor coefficients of sin / cos (small angle)
     double two_over_pi, pio2_hi, pio2_lo, trig_max;
     double ks[6], kc[6];                      // sin / cos kernels on [-pi/4, pi/4]
 };
@@ -87,10 +89,15 @@ __host__ __device__ inline K make_k() {
     k.inv_a0 = 1.0 / MASS;
     k.h_inv_a = H / (MASS + H * D_SLIDE);
     k.kd = 1.0 - k.h_inv_a * D_SLIDE;
-    k.h_mc_a = k.h_inv_a * MC;
-    k.rot_max = 0.0125;
+    k.g_h = GEAR / H;
+    k.q_x = k.h_inv_a * MC / (H * H);
+    k.al2_e = H * H * k.al_e[1];
+    k.al2_w = H * k.al_w[1];
+    k.al2_u = H * H * k.al_u[1];
+    k.inv_h = 1.0 / H;
+    k.rot_max = 0.01;
     k.s3 = -1.0 / 6.0; k.s5 = 1.0 / 120.0;
-    k.c2 = -0.5; k.c4 = 1.0 / 24.0; k.c6 = -1.0 / 720.0;
+    k.c2 = -0.5; k.c4 = 1.0 / 24.0; k.rot_max2 = k.rot_max * k.rot_max;
     k.two_over_pi = 0.63661977236758134308;
     k.pio2_hi = 1.5707963267948966;      // double(pi / 2)
     k.pio2_lo = 6.123233995736766e-17;   // pi / 2 - double(pi / 2)
@@ -109,29 +116,32 @@ static __device__ __noinline__ double2 sincos_cold(double psi) {   // (cos, sin)
     return make_double2(c, s);
 }
 
-// sin / cos of the heading at the start of an env step: two-constant Cody-Waite reduction (exact
-// products inside the FMAs) and the classical minimax kernels on [-pi/4, pi/4], every coefficient a
-// constant-bank operand.  <= 1 ulp for |x| < 1e5 (checked against libm); beyond that the library
-// routine (Payne-Hanek) runs out of line.  The library call inlined here cost ~85 instructions,
-// half of them moves of its fp64 literals.
+// sin / cos by a two-constant Cody-Waite reduction (exact products inside the FMAs) and the classical
+// minimax kernels on [-pi/4, pi/4], every coefficient a uniform-register operand.  <= 1 ulp for
+// |x| < 1e5 (checked against libm); the error of the reduction grows like |x| * 1e-33 beyond.
+__device__ __forceinline__ void sincos_cw(const K& k, double x, double& s, double& c) {
+    const double kq = rint(x * k.two_over_pi);
+    const int q = (int)(long long)kq;
+    double r = fma(-kq, k.pio2_hi, x);
+    r = fma(-kq, k.pio2_lo, r);
+    const double z = r * r;
+    double ps = fma(z, k.ks[5], k.ks[4]);
+    double pc = fma(z, k.kc[5], k.kc[4]);
+    ps = fma(z, ps, k.ks[3]); pc = fma(z, pc, k.kc[3]);
+    ps = fma(z, ps, k.ks[2]); pc = fma(z, pc, k.kc[2]);
+    ps = fma(z, ps, k.ks[1]); pc = fma(z, pc, k.kc[1]);
+    ps = fma(z, ps, k.ks[0]); pc = fma(z, pc, k.kc[0]);
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    s = (q & 2) ? -a : a;
+    c = ((q + 1) & 2) ? -b : b;
+}
+// Heading at the start of an env step: the library routine (Payne-Hanek) runs out of line beyond
+// 1e5 rad.  (The library call inlined here cost ~85 instructions, half of them moves of literals.)
 __device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double& c) {
     if (fabs(x) < k.trig_max) {
-        const double kq = rint(x * k.two_over_pi);
-        const int q = (int)kq;
-        double r = fma(-kq, k.pio2_hi, x);
-        r = fma(-kq, k.pio2_lo, r);
-        const double z = r * r;
-        double ps = fma(z, k.ks[5], k.ks[4]);
-        double pc = fma(z, k.kc[5], k.kc[4]);
-        ps = fma(z, ps, k.ks[3]); pc = fma(z, pc, k.kc[3]);
-        ps = fma(z, ps, k.ks[2]); pc = fma(z, pc, k.kc[2]);
-        ps = fma(z, ps, k.ks[1]); pc = fma(z, pc, k.kc[1]);
-        ps = fma(z, ps, k.ks[0]); pc = fma(z, pc, k.kc[0]);
-        const double sr = fma(r * z, ps, r);
-        const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-        const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
-        s = (q & 2) ? -a : a;
-        c = ((q + 1) & 2) ? -b : b;
+        sincos_cw(k, x, s, c);
     } else {
         const double2 cs = sincos_cold(x);
         c = cs.x;
@@ -139,58 +149,70 @@ __device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double
     }
 }
 
-// (c, s) <- rotation of (c, s) by the small angle a: Taylor series of sin / cos (|a| < 0.0125 ->
-// truncation below 1e-17), so the heading's sine / cosine follow the integrator without a
-// trigonometric call per substep.  Large steps (never reached: |omega| stays below ~4 rad/s, i.e.
-// |a| < 0.008) fall back to the exact evaluation at the new heading.
-__device__ __forceinline__ void rotate_cs(const K& k, double s3, double c4, double& c, double& s, double a,
-                                          double psi_new) {
-    if (fabs(a) < k.rot_max) {
-        const double x = a * a;
-        const double sd = a * fma(x, fma(x, k.s5, s3), 1.0);
-        const double cd = fma(x, fma(x, fma(x, k.c6, c4), k.c2), 1.0);
-        const double c2 = c * cd - s * sd;
-        s = fma(s, cd, c * sd);
-        c = c2;
-    } else {
-        const double2 cs = sincos_cold(psi_new);   // out of line: keeps the substep loop free of its constants
-        c = cs.x;
-        s = cs.y;
-    }
+// One mj_step.  The loop carries the heading increment a = h omega instead of omega (and x = a^2,
+// which the small-angle rotation needs anyway), with the constants rescaled accordingly.  With
+// u2 = c vy - s vx (lateral body velocity) and the servo error e clamped to +-flim,
+//     h^2 alpha = al2_e e + al2_w a + al2_u u2,        a <- a + h^2 alpha
+//     v <- (1 - h d / A) v + (h / A)(f + mc omega^2) (c, s) + (h mc / A) alpha (s, -c)
+// and (c, s) follow by the Taylor series of sin a / cos a (|a| < 0.01: truncation <= 1.4e-15, and
+// (c, s) restart from an exact sincos every env step).  30 fp64 operations.
+struct Sub {
+    double vx, vy, px, py, psi, a, x, c, s;
+};
+__device__ __forceinline__ void substep_core(const K& k, Sub& u, double fh, double cz) {
+    const double e = clamp_sym(fma(-k.g_h, u.a, cz), k.flim);  // velocity servo, kv = 1
+    const double qh = fma(k.q_x, u.x, fh);                      // thrust + centripetal term, along body x
+    const double u2 = fma(-u.s, u.vx, u.c * u.vy);
+    const double al2 = fma(k.al2_u, u2, fma(k.al2_w, u.a, k.al2_e * e));
+    const double mah = k.q_x * al2;
+    u.vx = fma(mah, u.s, fma(qh, u.c, k.kd * u.vx));
+    u.vy = fma(-mah, u.c, fma(qh, u.s, k.kd * u.vy));
+    u.a += al2;
+    u.px = fma(k.h, u.vx, u.px);
+    u.py = fma(k.h, u.vy, u.py);
+    u.psi += u.a;
+    u.x = u.a * u.a;
 }
 
-// opaque copy: pins a loop-invariant constant in a register (the compiler otherwise re-loads it from
-// the constant bank inside the substep loop whenever an FMA needs two constants)
-__device__ __forceinline__ double pin(double x) {
-    asm volatile("" : "+d"(x));
-    return x;
-}
-
-// Engine.step physics: ctrl already clipped to [-1, 1].  Returns cos / sin of the final heading
-// (one sincos at the start of the env step, ten incremental rotations).  With u2 = c vy - s vx,
-//     alpha = al_e e + al_w omega + al_u u2            (servo error e clamped to +-flim)
-//     v    <- (1 - h d / A) v + (h / A)(f + mc omega^2) (c, s) + (h mc / A) alpha (s, -c)
-// 33 fp64 operations per substep.
+// Engine.step physics: ctrl already clipped to [-1, 1].  Returns cos / sin of the final heading: one
+// sincos at the start of the env step, then (c, s) follow the integrator by incremental rotations.
 __device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx, double cz, double& c, double& s) {
     const double fh = k.h_inv_a * (k.gear * clamp_sym(cx, k.flim));  // site motor along body x, times h / A
-    const double flim = pin(k.flim), s3 = pin(k.s3), c4 = pin(k.c4);
-    sincos_k(k, d.psi, s, c);
-#pragma unroll 2
-    for (int i = 0; i < FRAME_SKIP; ++i) {
-        const double e = clamp_sym(fma(-k.gear, d.om, cz), flim);  // velocity servo, kv = 1
-        const double qh = fma(k.h_mc_a, d.om * d.om, fh);           // thrust + centripetal term, along body x
-        const double u2 = fma(-s, d.vx, c * d.vy);
-        const double al = fma(k.al_u[1], u2, fma(k.al_w[1], d.om, k.al_e[1] * e));
-        const double mah = k.h_mc_a * al;
-        d.vx = fma(mah, s, fma(qh, c, k.kd * d.vx));
-        d.vy = fma(-mah, c, fma(qh, s, k.kd * d.vy));
-        d.om = fma(k.h, al, d.om);
-        d.px = fma(k.h, d.vx, d.px);
-        d.py = fma(k.h, d.vy, d.py);
-        const double a = k.h * d.om;
-        d.psi += a;
-        rotate_cs(k, s3, c4, c, s, a, d.psi);
+    Sub u;
+    u.vx = d.vx; u.vy = d.vy; u.px = d.px; u.py = d.py; u.psi = d.psi;
+    u.a = k.h * d.om;
+    u.x = u.a * u.a;
+    sincos_k(k, d.psi, u.s, u.c);
+    int i = 0;
+    bool big = false;
+#pragma unroll
+    while (i < FRAME_SKIP) {
+        substep_core(k, u, fh, cz);
+        ++i;
+        if (!(u.x < k.rot_max2)) { big = true; break; }
+        const double sd = u.a * fma(u.x, fma(u.x, k.s5, k.s3), 1.0);
+        const double cd = fma(u.x, fma(u.x, k.c4, k.c2), 1.0);
+        const double c2 = u.c * cd - u.s * sd;
+        u.s = fma(u.s, cd, u.c * sd);
+        u.c = c2;
     }
+    // Remaining substeps with the heading evaluated directly (the last substep left (c, s) stale).
+    // Only reached for |omega| >= 5 rad/s, which the actuators cannot produce (steady state
+    // 3 rad/s) -- i.e. after a set_state with such a velocity.  Kept OUT of the hot loop on purpose:
+    // any cold code inside it (a call, or this inlined) made ptxas re-load 5-13 constants per substep;
+    // the hot loop is fully unrolled so that its constants are fetched once per env step.
+    if (big) {
+        sincos_cw(k, u.psi, u.s, u.c);
+#pragma unroll 1
+        for (; i < FRAME_SKIP; ++i) {
+            substep_core(k, u, fh, cz);
+            sincos_cw(k, u.psi, u.s, u.c);
+        }
+    }
+    d.vx = u.vx; d.vy = u.vy; d.px = u.px; d.py = u.py; d.psi = u.psi;
+    d.om = u.a * k.inv_h;
+    c = u.c;
+    s = u.s;
 }
 __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
     double c, s;
