@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_grad_tc_kernel(GradArgs A,
     tc::Pipe<KP> Q;
     tc::pipe_start<KP>(Q, A, S, O, threadIdx.x & 127, threadIdx.x >> 7, C.tower == 0);
     __syncthreads();
-    tc::minibatch<KP>(C, A, S, A.mb_stats, 0, Q, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
+    const tc::MbConst MK = tc::mb_const(A.mb_stats, 0, A.normalize_adv);
+    tc::minibatch<KP>(C, A, S, MK, 0, Q, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
     tc::teardown(C);
 }
 
@@ -946,15 +947,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
         w4 = load4(E.params);
     }
 
+    tc::MbConst MK = tc::mb_const(E.stats, 0, A.normalize_adv);
     for (int m = 0; m < n_mb; ++m) {
         // inputs of the reduction that do not depend on other CTAs: fetched ahead of the barrier
         const float share = E.rank_share ? __ldg(E.rank_share + m) : 1.f;
-        const float inv_cnt = (float)(1.0 / __ldg(E.stats + 3 * m + 2));
+        const float inv_cnt = MK.inv_b;
         MR_TR(2);
-        tc::minibatch<KP>(C, A, S, E.stats, m, Q, O, A.partials + (size_t)c * stride);
+        tc::minibatch<KP>(C, A, S, MK, m, Q, O, A.partials + (size_t)c * stride);
         MR_TR(3);
         grid_barrier(E.barrier, target, G);
         MR_TR(4);
+        if (m + 1 < n_mb) MK = tc::mb_const(E.stats, m + 1, A.normalize_adv);   // lands under the exchange below
 
         // ---- this CTA's slice of the gradient: sum over the CTAs of each parameter's tower -----------
         ++step;
