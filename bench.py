@@ -310,7 +310,8 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 
 # dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
-EPOCH_KERNEL_DRAM_BYTES = 151.8e6  # 144.7 MB read + 7.1 MB written (profiles/r01_ncu_full_final.txt)
+EPOCH_KERNEL_DRAM_BYTES = 149.8e6  # 145.5 MB read + 4.2 MB written (profiles/r01_ncu_full_final.txt)
+ENV_STEP_DRAM_BYTES = 837.4e6      # 351.8 MB read + 485.7 MB written at 2^22 envs (same capture)
 
 
 def time_epoch_kernel(model, dev):
@@ -375,7 +376,7 @@ def time_env_step_kernel(dev, peaks):
     achieved = ENV_STEP_BYTES * n / (ms * 1e-3) / 1e9
     env.close()
     return {"kernel": "point_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": ENV_STEP_DRAM_BYTES, "ms_per_launch": ms,
             "n_envs": n, "env_steps_per_s": n / (ms * 1e-3),
             "note": "algorithmic 145 B/env-step (SURVEY 8d); the state is fp64, physical traffic is 198 B/env-step (76 read, 122 written)"}
 
