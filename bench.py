@@ -57,11 +57,12 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.proc, self.lines, self.index = None, [], index
+        self.active = True   # only samples taken while a timed region runs are kept
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,7 +71,8 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            if self.active:
+                self.lines.append(line.strip())
 
     def stop(self):
         if self.proc is None:
@@ -227,8 +229,8 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     value = steps_per_iter * world * args.steps / (ms / 1e3)
+    sampler.active = False
 
     # ---- phase split and roofline of the dominant kernel (live CUDA events, same stream) -----------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -269,6 +271,7 @@ def run_ours(args):
     barrier()
     model.learn(total_timesteps=steps_per_iter * world * 3, reset_num_timesteps=True)  # warm (logger paths too)
     barrier()
+    sampler.active = True
     t0 = time.perf_counter()
     model.learn(total_timesteps=steps_per_iter * world * args.steps, reset_num_timesteps=True)
     barrier()
@@ -276,6 +279,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(wall, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_iter * world * args.steps / float(wall.item())
+    clocks = sampler.stop() if rank == 0 else None   # sampled every 20 ms inside the value and e2e timed regions
     h2d = N_EPOCHS * steps_per_iter * 8  # int64 permutations, pinned -> device, per rank
     d2h = EP_D2H_BYTES + 11 * 8
 

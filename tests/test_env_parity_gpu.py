@@ -139,3 +139,34 @@ def test_device_rng_streams_match_numpy(cuda_lib):
         n_goal_only += int((~full).sum())
         gpu.step(zero)
     assert n_goal_only > 0
+
+
+def test_point_fast_spin_and_large_heading_paths(cuda_lib):
+    """The env-step kernel's cold paths: |h omega| beyond the small-angle rotation (|omega| >= 5 rad/s, only
+    reachable through set_state) and headings beyond the Cody-Waite range (|psi| >= 1e5 rad: library sincos)."""
+    from mobrob_b200 import GpuVecEnv
+
+    n = 96
+    gpu = GpuVecEnv("point", n, seed=3, time_limit=None, terminate_on_goal=False)
+    gpu.reset()
+    st = gpu.get_state().cpu().numpy()
+    rng = np.random.default_rng(9)
+    st[:, 5] = np.where(np.arange(n) % 3 == 0, rng.uniform(-60, 60, n), st[:, 5])       # spin: up to 60 rad/s
+    st[:, 5] = np.where(np.arange(n) % 3 == 1, rng.uniform(4.9, 5.1, n), st[:, 5])      # straddles the switch
+    st[:, 2] = np.where(np.arange(n) % 4 == 0, rng.uniform(-3e5, 3e5, n), st[:, 2])     # hinge angle: huge heading
+    st[:, 3:5] = rng.uniform(-2, 2, (n, 2))
+    gpu.set_state(torch.as_tensor(st))
+    body = po.PointBody(n)
+    body.q[:] = st[:, 0:3]; body.v[:] = st[:, 3:6]; body.body_xy[:] = st[:, 6:8]
+    body.psi0[:] = st[:, 8]; body.ctrl[:] = st[:, 9:11]
+    goal = st[:, 11:13].astype(np.float32)
+    for t in range(12):
+        a = np.sign(rng.standard_normal((n, 2))).astype(np.float32)
+        body.step(a)
+        o_gpu, _, d, _ = gpu.step(a)
+        assert not d.any()
+        np.testing.assert_allclose(o_gpu, body.obs(goal), rtol=RTOL, atol=2e-6, err_msg=f"obs step {t}")
+    got = gpu.get_state().cpu().numpy()[:, :11]
+    ref = body.state_vector()
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < RTOL, err.max()

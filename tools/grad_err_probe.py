@@ -30,3 +30,10 @@ for (O, TT, N, B, pre) in [(14, 16, 40, 100, False), (14, 64, 37, 999, True), (2
     g = up.compute_grad(dbuf, dperm[:B], stats[0], N, TT).cpu().numpy()[:up.n_params]
     print(f"O={O} T={TT} N={N} B={B} pretrained={pre}: max|g - g_ref| / max|g_ref| = "
           f"{np.abs(g - g_ref).max() / np.abs(g_ref).max():.2e}")
+    off, parts = 0, []
+    for name in sb3_oracle.PARAM_ORDER:   # every tensor against its own largest entry
+        n = dict(pol.named_parameters())[name].numel()
+        r = g_ref[off:off + n]
+        parts.append(f"{name.replace('mlp_extractor.', '')} {np.abs(g[off:off + n] - r).max() / max(np.abs(r).max(), 1e-30):.1e}")
+        off += n
+    print("      per tensor: " + ", ".join(parts))
