@@ -62,37 +62,49 @@ extern "C" int mr_host_permutation(uint64_t seed, uint64_t stream, int64_t n, in
     int bits = 0;
     while ((n >> bits) > 8192 && bits < 12) ++bits;
     const int K = 1 << bits;
-    std::vector<uint32_t> tmp((size_t)n);
+    // scratch lives with the calling thread (the feeder's workers call this ten times per iteration:
+    // fresh vectors cost an allocation and first-touch page faults on 7 MB every time)
+    static thread_local std::vector<uint32_t> tmp;
+    static thread_local std::vector<uint16_t> key;
+    if (tmp.size() < (size_t)n) tmp.resize((size_t)n);
     if (K > 1) {
-        std::vector<uint8_t> key8;
-        std::vector<uint16_t> key((size_t)n);
-        std::vector<int64_t> count(K + 1, 0);
-        for (int64_t i = 0; i < n;) {   // 64 random bits -> up to 5 keys of <= 12 bits
+        if (key.size() < (size_t)n) key.resize((size_t)n);
+        int64_t count[4097];
+        int64_t head[4096];
+        for (int b = 0; b <= K; ++b) count[b] = 0;
+        const int per = 64 / (bits > 0 ? bits : 1);   // keys per 64 random bits
+        const uint64_t mask = (uint64_t)(K - 1);
+        for (int64_t i = 0; i < n;) {
             uint64_t r = g.next();
-            for (int q = 0; q < 5 && i < n; ++q, ++i, r >>= 12) {
-                const uint16_t b = (uint16_t)(r & (uint64_t)(K - 1));
+            for (int q = 0; q < per && i < n; ++q, ++i, r >>= bits) {
+                const uint16_t b = (uint16_t)(r & mask);
                 key[(size_t)i] = b;
                 ++count[b + 1];
             }
         }
         for (int b = 0; b < K; ++b) count[b + 1] += count[b];
-        std::vector<int64_t> head(count.begin(), count.end() - 1);
-        for (int64_t i = 0; i < n; ++i) tmp[(size_t)head[key[(size_t)i]]++] = (uint32_t)i;
+        for (int b = 0; b < K; ++b) head[b] = count[b];
+        uint32_t* t = tmp.data();
+        const uint16_t* kk = key.data();
+        for (int64_t i = 0; i < n; ++i) t[head[kk[i]]++] = (uint32_t)i;
         for (int b = 0; b < K; ++b) {
-            uint32_t* a = tmp.data() + count[b];
+            uint32_t* a = t + count[b];
             const int64_t len = count[b + 1] - count[b];
             for (int64_t i = len - 1; i > 0; --i) {
                 const uint32_t j = g.below((uint32_t)i + 1);
-                const uint32_t t = a[i]; a[i] = a[j]; a[j] = t;
+                const uint32_t v = a[i]; a[i] = a[j]; a[j] = v;
             }
+            int64_t* o = out + count[b];   // widen while the bucket is still in cache
+            for (int64_t i = 0; i < len; ++i) o[i] = (int64_t)a[i];
         }
     } else {
-        for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = (uint32_t)i;
+        uint32_t* t = tmp.data();
+        for (int64_t i = 0; i < n; ++i) t[i] = (uint32_t)i;
         for (int64_t i = n - 1; i > 0; --i) {
             const uint32_t j = g.below((uint32_t)i + 1);
-            const uint32_t t = tmp[(size_t)i]; tmp[(size_t)i] = tmp[j]; tmp[j] = t;
+            const uint32_t v = t[i]; t[i] = t[j]; t[j] = v;
         }
+        for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)t[i];
     }
-    for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)tmp[(size_t)i];
     return MR_OK;
 }
