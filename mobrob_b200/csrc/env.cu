@@ -69,7 +69,8 @@ point_step_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act,
         const int64_t bp = block + pf_dist / STEP_THREADS;   // the block that starts one wave later
         if (bp >= 0 && bp < (int64_t)gridDim.x) {
             st.prefetch_tile(bp, threadIdx.x);
-            if (threadIdx.x >= 120) asm volatile("prefetch.global.L2 [%0];" ::"l"(act + bp * STEP_THREADS + (threadIdx.x - 120) * 16));
+            const int64_t a0 = bp * STEP_THREADS + (int64_t)(threadIdx.x - 120) * 16;   // 16 float2 = one 128-byte line
+            if (threadIdx.x >= 120 && a0 + 16 <= st.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(act + a0));
         }
     }
     if (i < st.n) {

@@ -43,9 +43,6 @@ struct Dyn {
     double px, py, psi, vx, vy, om;
 };
 
-__device__ __forceinline__ double clampd(double x, double lo, double hi) {
-    return fmin(fmax(x, lo), hi);
-}
 // clamp to [-lim, lim]: one compare on |x| and a select (fmin / fmax on fp64 carry NaN-propagation
 // code: 18 instructions per clamp in the substep loop, profiles/r01 SASS)
 __device__ __forceinline__ double clamp_sym(double x, double lim) {
