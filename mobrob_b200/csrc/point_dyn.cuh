@@ -45,7 +45,7 @@ struct Dyn {
 
 // clamp to [-lim, lim]: one compare on |x| and a select (fmin / fmax on fp64 carry NaN-propagation
 // code: 18 instructions per clamp in the substep loop, profiles/r01 SASS)
-__device__ __forceinline__ double clamp_sym(double x, double lim) {
+__host__ __device__ __forceinline__ double clamp_sym(double x, double lim) {
     return fabs(x) > lim ? copysign(lim, x) : x;
 }
 
@@ -107,16 +107,23 @@ __host__ __device__ inline K make_k() {
     return k;
 }
 
-static __device__ __noinline__ double2 sincos_cold(double psi) {   // (cos, sin), by value: no stack slot
+// (the integrator's functions are __host__ __device__: tests/test_point_dyn_host_cpu.py compiles this
+// header into a host program and checks it against the oracle without a GPU)
+static __host__ __device__ __noinline__ double2 sincos_cold(double psi) {   // (cos, sin), by value: no stack slot
     double s, c;
+#ifdef __CUDA_ARCH__
     sincos(psi, &s, &c);
+#else
+    s = ::sin(psi);
+    c = ::cos(psi);
+#endif
     return make_double2(c, s);
 }
 
 // sin / cos by a two-constant Cody-Waite reduction (exact products inside the FMAs) and the classical
 // minimax kernels on [-pi/4, pi/4], every coefficient a uniform-register operand.  <= 1 ulp for
 // |x| < 1e5 (checked against libm); the error of the reduction grows like |x| * 1e-33 beyond.
-__device__ __forceinline__ void sincos_cw(const K& k, double x, double& s, double& c) {
+__host__ __device__ __forceinline__ void sincos_cw(const K& k, double x, double& s, double& c) {
     const double kq = rint(x * k.two_over_pi);
     const int q = (int)(long long)kq;
     double r = fma(-kq, k.pio2_hi, x);
@@ -136,7 +143,7 @@ __device__ __forceinline__ void sincos_cw(const K& k, double x, double& s, doubl
 }
 // Heading at the start of an env step: the library routine (Payne-Hanek) runs out of line beyond
 // 1e5 rad.  (The library call inlined here cost ~85 instructions, half of them moves of literals.)
-__device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double& c) {
+__host__ __device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double& c) {
     if (fabs(x) < k.trig_max) {
         sincos_cw(k, x, s, c);
     } else {
@@ -156,7 +163,7 @@ __device__ __forceinline__ void sincos_k(const K& k, double x, double& s, double
 struct Sub {
     double vx, vy, px, py, psi, a, x, c, s;
 };
-__device__ __forceinline__ void substep_core(const K& k, Sub& u, double fh, double cz) {
+__host__ __device__ __forceinline__ void substep_core(const K& k, Sub& u, double fh, double cz) {
     const double e = clamp_sym(fma(-k.g_h, u.a, cz), k.flim);  // velocity servo, kv = 1
     const double qh = fma(k.q_x, u.x, fh);                      // thrust + centripetal term, along body x
     const double u2 = fma(-u.s, u.vx, u.c * u.vy);
@@ -173,7 +180,7 @@ __device__ __forceinline__ void substep_core(const K& k, Sub& u, double fh, doub
 
 // Engine.step physics: ctrl already clipped to [-1, 1].  Returns cos / sin of the final heading: one
 // sincos at the start of the env step, then (c, s) follow the integrator by incremental rotations.
-__device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx, double cz, double& c, double& s) {
+__host__ __device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx, double cz, double& c, double& s) {
     const double fh = k.h_inv_a * (k.gear * clamp_sym(cx, k.flim));  // site motor along body x, times h / A
     Sub u;
     u.vx = d.vx; u.vy = d.vy; u.px = d.px; u.py = d.py; u.psi = d.psi;
@@ -223,7 +230,7 @@ __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
 // u = R^T v the accelerometer is a1 = (q - d u1) / m, a2 = -(d u2 + mc alpha) / m.
 // goal_norm: ||goal - pos|| (the reference divides by the norm of the ROTATED vector, equal to it up
 // to rounding far below float32; the env step has it already for the reward).
-__device__ __forceinline__ void sensors_cs(const K& k, const Dyn& d, double c, double s, double cx, double cz,
+__host__ __device__ __forceinline__ void sensors_cs(const K& k, const Dyn& d, double c, double s, double cx, double cz,
                                            float gx, float gy, float* o, double goal_norm) {
     const double f = k.gear * clamp_sym(cx, k.flim);
     const double e = clamp_sym(fma(-k.gear, d.om, cz), k.flim);
