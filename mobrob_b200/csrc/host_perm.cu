@@ -58,9 +58,12 @@ extern "C" int mr_host_permutation(uint64_t seed, uint64_t stream, int64_t n, in
     MR_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "n out of range");
     if (n == 0) return MR_OK;
     Xoshiro g(seed, stream);
-    // buckets of ~8K indices (32 KB as uint32: L1/L2 resident)
+    // Buckets of <= 64K indices (256 KB as uint32: L2 resident).  Smaller buckets shuffle faster (L1) but
+    // need more write streams in the deal, and beyond ~32 concurrent streams the deal falls off a cliff on
+    // the hosts measured (1.4 ns per index at 16 streams, 6-8 ns at 64+): at n = 1.2 M, 32 buckets take
+    // 8 ms per permutation, 256 buckets 19 ms.
     int bits = 0;
-    while ((n >> bits) > 8192 && bits < 12) ++bits;
+    while ((n >> bits) > 65536 && bits < 12) ++bits;
     const int K = 1 << bits;
     // scratch lives with the calling thread (the feeder's workers call this ten times per iteration:
     // fresh vectors cost an allocation and first-touch page faults on 7 MB every time)
