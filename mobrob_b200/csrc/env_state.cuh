@@ -108,10 +108,11 @@ struct PointState {
         char* p = slot(i);
         return make_double2(at<double>(p, F_PX), at<double>(p, F_PY));
     }
-    // pull tile t (one block's whole hot input, 76 lines of 128 B) towards L2; called by a block one
-    // wave ahead of the tile's use, thread k takes line k
+    // pull tile t (one block's hot input: 68 of the tile's 76 lines of 128 B -- the step never reads the ctrl
+    // field) towards L2; called by a block one wave ahead of the tile's use, thread k takes line k
     __device__ __forceinline__ void prefetch_tile(int64_t t, int k) const {
-        if (k < TILE_BYTES / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile(t) + k * 128));
+        const bool ctrl_line = k >= F_CTRL / 128 && k < F_GOAL / 128;
+        if (k < TILE_BYTES / 128 && !ctrl_line) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile(t) + k * 128));
     }
 };
 
