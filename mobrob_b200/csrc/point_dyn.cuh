@@ -182,33 +182,38 @@ __host__ __device__ __forceinline__ void substep_core(const K& k, Sub& u, double
 // sincos at the start of the env step, then (c, s) follow the integrator by incremental rotations.
 __host__ __device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx, double cz, double& c, double& s) {
     const double fh = k.h_inv_a * (k.gear * clamp_sym(cx, k.flim));  // site motor along body x, times h / A
+    const Dyn d0 = d;   // only the cold path below reads it
     Sub u;
     u.vx = d.vx; u.vy = d.vy; u.px = d.px; u.py = d.py; u.psi = d.psi;
     u.a = k.h * d.om;
     u.x = u.a * u.a;
     sincos_k(k, d.psi, u.s, u.c);
-    int i = 0;
-    bool big = false;
+    const double c_start = u.c, s_start = u.s;
+    // The ten substeps are ONE straight-line block: no branch, no call, no cold code inside (a call made
+    // every constant caller-saved; an in-loop exit branch kept them out of the uniform registers).  The
+    // small-angle condition is only accumulated.
+    bool big = !(u.x < k.rot_max2);
 #pragma unroll
-    while (i < FRAME_SKIP) {
+    for (int i = 0; i < FRAME_SKIP; ++i) {
         substep_core(k, u, fh, cz);
-        ++i;
-        if (!(u.x < k.rot_max2)) { big = true; break; }
+        big |= !(u.x < k.rot_max2);
         const double sd = u.a * fma(u.x, fma(u.x, k.s5, k.s3), 1.0);
         const double cd = fma(u.x, fma(u.x, k.c4, k.c2), 1.0);
         const double c2 = u.c * cd - u.s * sd;
         u.s = fma(u.s, cd, u.c * sd);
         u.c = c2;
     }
-    // Remaining substeps with the heading evaluated directly (the last substep left (c, s) stale).
-    // Only reached for |omega| >= 5 rad/s, which the actuators cannot produce (steady state
-    // 3 rad/s) -- i.e. after a set_state with such a velocity.  Kept OUT of the hot loop on purpose:
-    // any cold code inside it (a call, or this inlined) made ptxas re-load 5-13 constants per substep;
-    // the hot loop is fully unrolled so that its constants are fetched once per env step.
+    // Some |h omega| was beyond the small-angle rotation (|omega| >= 5 rad/s, which the actuators cannot
+    // produce: steady state 3 rad/s -- i.e. after a set_state with such a velocity): redo the env step
+    // from the saved state with the heading evaluated directly every substep.
     if (big) {
-        sincos_cw(k, u.psi, u.s, u.c);
+        u.vx = d0.vx; u.vy = d0.vy; u.px = d0.px; u.py = d0.py; u.psi = d0.psi;
+        u.a = k.h * d0.om;
+        u.x = u.a * u.a;
+        u.c = c_start;
+        u.s = s_start;
 #pragma unroll 1
-        for (; i < FRAME_SKIP; ++i) {
+        for (int i = 0; i < FRAME_SKIP; ++i) {
             substep_core(k, u, fh, cz);
             sincos_cw(k, u.psi, u.s, u.c);
         }
