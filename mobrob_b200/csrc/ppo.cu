@@ -1246,7 +1246,7 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
         perm_to_rows_kernel<<<ceil_div(mb_size, 256), 256, 0, s>>>(perm, mb_size, N, T, rows);
         MR_CHECK_LAUNCH();
         A.rows = rows;
-        // obs_dim + 1 (bias column) padded to the bf16 MMA K of 16
+        // obs_dim + 1 (bias column) padded to the 16-bit MMA K of 16
         const int kp = obs_dim + 1 <= 16 ? 16 : 32;
         const int64_t tiles = (mb_size + tc::TILE - 1) / tc::TILE;
         grid = (int)std::min<int64_t>(2 * tiles, max_parts & ~1);

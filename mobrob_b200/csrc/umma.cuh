@@ -1,8 +1,9 @@
-// sm_100a tensor-core plumbing used by the PPO update kernel: tcgen05.mma (kind::tf32) with
+// sm_100a tensor-core plumbing used by the PPO update kernel: tcgen05.mma (kind::f16 on fp16 operand
+// pairs in the product path, ppo_tc.cuh; kind::tf32 for the layout probes) with
 // shared-memory operand descriptors, tensor-memory (TMEM) allocation and loads, mbarrier
 // completion, and the shared-memory operand layout both major modes can read.
 //
-// Operand layout ("panel"): a panel is R rows of 128 bytes (32 tf32 values); inside every
+// Operand layout ("panel"): a panel is R rows of 128 bytes (32 tf32 or 64 fp16 values); inside every
 // 8-row group the 16-byte chunks of a row are XOR-swizzled with (row & 7) -- the hardware's
 // SWIZZLE_128B pattern, so panels must start on 1024-byte boundaries.  The same bytes are a valid
 //   * K-major operand   : row = M/N index, the 32 values of a row = 32 consecutive K
