@@ -315,7 +315,7 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 # dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
 EPOCH_KERNEL_DRAM_BYTES = 149.8e6  # 145.5 MB read + 4.2 MB written (profiles/r01_ncu_full_final.txt)
-ENV_STEP_DRAM_BYTES = 837.4e6      # 351.8 MB read + 485.7 MB written at 2^22 envs (same capture)
+ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
 def time_epoch_kernel(model, dev):
