@@ -124,7 +124,12 @@ int mr_gae(const float* rew, const float* val, const float* ep_start, const floa
 int mr_ppo_num_params(int obs_dim);  /* 10437 (point) / 11973 (car) */
 int mr_ppo_grad_stride(int obs_dim); /* floats in a gradient vector incl. the 16-slot stats tail:
                                         [policy_loss, value_loss, clip_fraction, approx_kl, ...] */
-int mr_ppo_max_parts(void);          /* CTAs mr_ppo_grad may use = rows of `partials` */
+int mr_ppo_max_parts(void);          /* CTAs the update kernels use on the current device.  The `partials`
+                                        scratch below holds (mr_ppo_max_parts() + 1) rows of
+                                        mr_ppo_grad_stride() floats; it is caller-owned, and everything a
+                                        launch synchronises through lives in it (two updaters on different
+                                        streams never share state inside the library) */
+int mr_ppo_epoch_scratch_floats(int obs_dim); /* part of `partials` mr_ppo_epoch_fused zeroes per launch */
 
 /* (sum adv, sum adv^2, count) per minibatch of one epoch's permutation -> stats [n_mb][3] f64.
  * With several ranks the host all-reduces stats so that normalisation is over the global
@@ -134,21 +139,22 @@ int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, i
 
 /* evaluate_actions + loss + analytic backward for one minibatch (perm points at its slice).
  * mb_stats = the minibatch's (global) stats triple.  rank_share = local count / global count.
- * partials [mr_ppo_max_parts()][stride] scratch; grad [stride] out: d(loss)/d(params) of this
+ * rows [mb_size] int32 caller-owned scratch (the samples as time-major buffer rows t * N + n);
+ * partials [mr_ppo_max_parts() + 1][stride] scratch; grad [stride] out: d(loss)/d(params) of this
  * rank's share (sum over ranks = SB3's gradient) followed by the stats tail. */
 int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
                 const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
-                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
-                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
+                int32_t* rows, int64_t mb_size, const double* mb_stats, int64_t N, int64_t T,
+                float clip_range, float ent_coef, float vf_coef, int normalize_adv, float rank_share,
                 float* partials, float* grad, void* stream);
 
 /* The forward/backward kernel of mr_ppo_grad alone: per-CTA partial gradients, no reduction
  * (*n_parts rows of `partials` are valid).  Exposed so bench.py can time the dominant kernel. */
 int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, const float* act,
                          const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
-                         int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
-                         float ent_coef, float vf_coef, int normalize_adv, float* partials, int* n_parts,
-                         void* stream);
+                         int32_t* rows, int64_t mb_size, const double* mb_stats, int64_t N, int64_t T,
+                         float clip_range, float ent_coef, float vf_coef, int normalize_adv, float* partials,
+                         int* n_parts, void* stream);
 
 /* clip_grad_norm_(max_grad_norm) then torch.optim.Adam.step (eps as given; SB3 uses 1e-5).
  * step: device int64[2]: [0] = Adam step count (state["step"]), incremented; [1] = launch-internal
@@ -183,28 +189,33 @@ int mr_rollout(mr_env* env, const float* params, int64_t T, float* last_obs, flo
  * mr_ppo_adv_stats; info [n_mb][8] receives mr_adam_step's info rows (may be NULL). */
 int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
                        const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
-                       const double* stats, int64_t N, int64_t T, float clip_range, float ent_coef,
-                       float vf_coef, int normalize_adv, float lr, float beta1, float beta2, float eps,
-                       float max_grad_norm, float* partials, float* grad, float* info, void* stream);
+                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       int64_t batch_size, const double* stats, int64_t N, int64_t T, float clip_range,
+                       float ent_coef, float vf_coef, int normalize_adv, float lr, float beta1, float beta2,
+                       float eps, float max_grad_norm, float* partials, float* grad, float* info, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused epoch: every minibatch of one epoch of PPO.train in ONE cooperative launch (forward,
- * backward, gradient reduction, [all-reduce,] clip_grad_norm_, Adam; grid barriers in between).
- * With xchg != NULL the per-minibatch gradient all-reduce (the reference has none: SB3 trains in
- * one process) runs inside the kernel over NVLink peer memory: each CTA pushes its slice of the
- * gradient into every peer's inbox, raises a flag, and sums the ranks' slices in rank order.
- * rank_share [n_mb] device floats (local / global minibatch count) or NULL. */
+ * backward, gradient reduction, [all-reduce,] clip_grad_norm_, Adam; one grid barrier per
+ * minibatch, two with several ranks).  With xchg != NULL the per-minibatch gradient all-reduce
+ * (the reference has none: SB3 trains in one process) runs inside the kernel over NVLink peer
+ * memory: each CTA pushes its slice of the reduced gradient into every peer's inbox as tagged
+ * packets and sums the ranks' slices in rank order (parameters stay bit-identical on all ranks).
+ * A peer that stops delivering ends the wait after ~4 s and raises the flag mr_xchg_status reads.
+ * rows [n_samples] int32 caller-owned scratch.  rank_share [n_mb] device floats (local / global
+ * minibatch count) or NULL. */
 typedef struct mr_xchg mr_xchg;
 /* Allocate this rank's inbox; h_handle_out receives its 64-byte CUDA IPC handle. */
 int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out);
 /* h_all_handles [world][64]: every rank's handle (gathered by the host, e.g. torch.distributed). */
 int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles);
 void mr_xchg_destroy(mr_xchg* x);
+/* *timed_out <- 1 if an in-kernel exchange gave up waiting for a peer since creation (synchronous read) */
+int mr_xchg_status(mr_xchg* x, int* timed_out);
 int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
                        const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
-                       const double* stats, const float* rank_share, int64_t N, int64_t T,
+                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       int64_t batch_size, const double* stats, const float* rank_share, int64_t N, int64_t T,
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream);

@@ -37,21 +37,23 @@ _SIGNATURES = {
     "mr_ppo_num_params": (c_int, [c_int]),
     "mr_ppo_grad_stride": (c_int, [c_int]),
     "mr_ppo_max_parts": (c_int, []),
+    "mr_ppo_epoch_scratch_floats": (c_int, [c_int]),
     "mr_ppo_adv_stats": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
-    "mr_ppo_grad": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
+    "mr_ppo_grad": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
                             c_float, c_float, c_float, c_int, c_float, _P, _P, _P]),
-    "mr_ppo_train_epoch": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P,
+    "mr_ppo_train_epoch": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P,
                                    c_int64, c_int64, c_float, c_float, c_float, c_int, c_float, c_float,
                                    c_float, c_float, c_float, _P, _P, _P, _P]),
     "mr_xchg_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p), _P]),
     "mr_xchg_connect": (c_int, [_P, _P]),
     "mr_xchg_destroy": (None, [_P]),
-    "mr_ppo_epoch_fused": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P,
+    "mr_xchg_status": (c_int, [_P, POINTER(c_int)]),
+    "mr_ppo_epoch_fused": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P,
                                    c_int64, c_int64, c_float, c_float, c_float, c_int, c_float, c_float,
                                    c_float, c_float, c_float, _P, _P, _P, _P, _P]),
     "mr_rollout": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,
                            c_uint64, c_int64, c_double, _P, _P, _P, c_int, _P]),
-    "mr_ppo_grad_partials": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
+    "mr_ppo_grad_partials": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
                                      c_float, c_float, c_float, c_int, _P, _P, _P]),
     "mr_rollout_unfused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,
                                    c_uint64, c_int64, c_double, _P, _P, _P, c_int, _P]),
@@ -68,11 +70,23 @@ def exported_symbols():
 
 
 def load():
-    """dlopen the library (building it first if sources are newer) and declare signatures."""
+    """dlopen the library and declare signatures.  A library older than its sources is rebuilt
+    first when nvcc is on PATH (so tests and bench.py never run a stale .so after an edit of
+    csrc/); without nvcc that is an error, not a silent stale run."""
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("MR_LIB_PATH", _build.LIB_PATH)  # MR_LIB_PATH: debug variants (tools/trace_epoch.py)
+    path = os.environ.get("MR_LIB_PATH")  # MR_LIB_PATH: debug variants (tools/trace_epoch.py), used as they are
+    if path is None:
+        path = _build.LIB_PATH
+        if _build.needs_build():
+            import shutil
+
+            if shutil.which(os.environ.get("NVCC", "nvcc")):
+                _build.build()
+            elif os.path.exists(path):
+                raise RuntimeError(f"{path} is older than mobrob_b200/csrc (or include/): rebuild it with "
+                                   "`python -m mobrob_b200.build`; nvcc is not on PATH here.")
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: run `python -m mobrob_b200.build` (or __graft_entry__.build()). "

@@ -44,6 +44,39 @@ void count_launch(uint64_t n = 1);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (dynamic shared-memory opt-in) and SM counts are per DEVICE, and one process
+// may drive several devices through this ABI (mr_env_create / mr_xchg_create take a device index):
+// one-time setup is keyed by the current device, never by a process-wide flag.
+constexpr int MR_MAX_DEVICES = 64;
+struct OncePerDevice {
+    bool done[MR_MAX_DEVICES] = {};
+    // true the first time it is asked about the current device (dev receives its index)
+    bool first(int* dev_out = nullptr) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MR_MAX_DEVICES) dev = 0;
+        if (dev_out) *dev_out = dev;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+static inline int sm_count() {
+    static int sms[MR_MAX_DEVICES] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MR_MAX_DEVICES) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev] ? sms[dev] : 148;
+}
+// entry points that must run on a handle's device switch to it for the call only
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---------------------------------------------------------------------------------------
 // PCG64 (numpy's default BitGenerator) -- gymnasium Box.sample draws from
 // Generator(PCG64(SeedSequence(seed))).uniform(low, high)  [GYM 0.28.1; call sites

@@ -360,7 +360,7 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
         set_error("unknown env kind %d (0 = point, 1 = car)", kind);
         return MR_ERR_UNSUPPORTED;
     }
-    MR_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);   // the caller's current device is left as it was
     mr_env* e = new mr_env();
     e->kind = kind;
     e->n = n_envs;
@@ -389,7 +389,7 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
 
 void mr_env_destroy(mr_env* env) {
     if (!env) return;
-    cudaSetDevice(env->device);
+    DeviceGuard guard(env->device);
     cudaFree(env->slab);
     if (env->scratch) cudaFree(env->scratch);
     delete env;
@@ -414,7 +414,7 @@ int mr_env_seed(mr_env* env, const uint64_t* h_pcg_init, const uint64_t* h_pcg_g
                 const int64_t* h_engine_seed, void* stream) {
     MR_REQUIRE(env && h_pcg_init && h_pcg_goal && h_engine_seed, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
-    MR_CUDA(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
     const EnvCold& c = cold_of(env);
     MR_CUDA(cudaMemcpyAsync(c.pcg_init, h_pcg_init, env->n * 32, cudaMemcpyHostToDevice, s));
     MR_CUDA(cudaMemcpyAsync(c.pcg_goal, h_pcg_goal, env->n * 32, cudaMemcpyHostToDevice, s));

@@ -57,15 +57,11 @@ extern "C" int mr_policy_forward(const float* params, int obs_dim, const float* 
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     if (n <= 0) return MR_OK;
     size_t smem = (smem_w_floats(obs_dim) + PF_WARPS * (MAX_OBS * PF_E + 128 * PF_E)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice once;
+    if (once.first())
         MR_CUDA(cudaFuncSetAttribute(policy_forward_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     int64_t tiles = (n + PF_E - 1) / PF_E;
     int blocks = (int)std::min<int64_t>((tiles + PF_WARPS - 1) / PF_WARPS, (int64_t)sms * 2);
     policy_forward_kernel<<<blocks, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(

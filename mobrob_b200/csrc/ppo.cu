@@ -691,6 +691,7 @@ __global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ 
 // parameters stay bit-identical across ranks.
 struct PeerXchg {
     int world, rank;
+    int* err;                           // set to 1 when a peer's packets did not arrive in time
     unsigned long long* inbox;          // local  [2][world][stride] packets {seq << 32 | float bits}
     unsigned long long* peer_inbox[8];  // peers' inboxes (NVLink-mapped)
 };
@@ -705,7 +706,9 @@ struct EpochArgs {
     float lr, beta1, beta2, eps, max_grad_norm;
     float* grad;               // [stride] last reduced gradient
     float* info;               // [n_mb][8] or NULL
-    double* sq;                // [n_cta] scratch
+    double* sq;                // [n_cta] scratch (v1 kernel)
+    float* acc;                // [3][2 * TL.size] rotating gradient accumulators (zero at launch)
+    float* gsum;               // [2 * TL.size] gradient summed over ranks (world > 1)
     unsigned* barrier;         // [1], zero at launch
     unsigned seq0;             // exchange sequence number before this launch
     PeerXchg X;
@@ -893,7 +896,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) ppo_epoch_kernel(EpochArgs E, i
 // shaped to pay it once each.  (Tried and measured slower: every CTA applying Adam to its whole
 // tower to save the third barrier -- 4 x the L2 traffic, 15 us instead of 10 us per minibatch.)
 template <int KP>
-__global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs E, int O) {
+__global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_v1_kernel(EpochArgs E, int O) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ float4 s_grp[tc::THREADS];
     __shared__ float4 s_x[8 * 32];   // peers' packets of the own threads (tid < q4 <= 32)
@@ -1158,6 +1161,264 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
     tc::teardown(C);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core epoch kernel, second form (round 2).  What changed against ppo_epoch_tc_v1_kernel is
+// everything BETWEEN the tiles of consecutive minibatches -- 47 % of the v1 kernel's time:
+//   v1: 148 partial vectors -> L2 | barrier | every CTA pulls its 72-float slice from 74 partials |
+//       barrier | clip + Adam on the slice | barrier | every CTA pulls its tower's new parameters.
+//   now: every CTA adds its partial into ONE accumulator with a single bulk reduction
+//       (cp.reduce.async.bulk .add.f32, shared -> L2, 22 KB) | ONE barrier | every CTA reads the
+//       whole reduced gradient (one wave of 12 float4 loads per thread), derives the clip
+//       coefficient itself and applies Adam to ITS tower, whose fp32 master copy and moments live in
+//       its shared memory for the whole epoch (74-fold redundant arithmetic instead of two more
+//       grid-wide hand-offs); the updated W2 goes straight from the Adam registers into the fp16
+//       operand panel.
+// Three accumulators rotate (minibatch m uses m % 3; after barrier j the CTAs clear their slices of
+// buffer (j - 1) % 3, whose readers all passed barrier j - 1 ... j).  The order in which the L2
+// adds the 74 contributions is not fixed, so a single-GPU run is reproducible to rounding only
+// (1e-7 of the gradient); every CTA reads the same sums, so the towers' copies -- and with more
+// than one rank, the ranks -- stay bit-identical.
+// World > 1: after the barrier the owner of each accumulator slice pushes it to every peer (tagged
+// 8-byte packets over NVLink, as in v1), sums the peers' slices in rank order into `gsum`, and a
+// second barrier publishes the global sum.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(umma::smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // async-proxy writes before the generic release below
+}
+
+template <int KP>
+__global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs E, int O) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ double s_sq[tc::WARPS];
+    __shared__ float4 s_x[8 * 32];   // peers' packets of the slice threads (tid < q4 <= 32)
+    const ParamLayout L = make_layout(O);
+    const tc::TowerLayout TL = tc::make_tl(O);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int n_mb = (int)((E.n_samples + E.batch - 1) / E.batch);
+    const int acc_floats = 2 * TL.size;
+    const int nq = acc_floats >> 2;        // quads of the accumulator
+    const int q4 = (nq + G - 1) / G;       // quads per CTA slice (<= 32, checked on the host)
+    const int my_quad = c * q4 + tid;
+    const bool slice_t = tid < q4 && my_quad < nq;
+    unsigned target = 0;
+    int64_t step = E.step[0];
+    double b1pow = pow((double)E.beta1, (double)step), b2pow = pow((double)E.beta2, (double)step);
+
+    MR_TR(0);
+    tc::Ctx C = tc::make_ctx(smem_raw, c & 1);
+    tc::setup(C);
+    float* st_w = reinterpret_cast<float*>(C.base + tc::OFF_STATE);
+    float* st_m = st_w + TL.size;
+    float* st_v = st_m + TL.size;
+    float* stage = reinterpret_cast<float*>(C.base + tc::OFF_H1);   // H1 + dZ panels are idle between minibatches
+    C.p_b2 = st_w + TL.b2;
+    C.p_hw = st_w + TL.hw;
+    C.p_hs = st_w + TL.hs;
+    GradArgs A = E.G;
+    const tc::Sched S{E.n_samples, E.batch, n_mb, c >> 1, G >> 1};
+    tc::Pipe<KP> Q;
+    tc::pipe_start<KP>(Q, A, S, O, tid & 127, tid >> 7, C.tower == 0);
+
+    // the tower's parameters and Adam moments: flat global arrays -> shared memory, TL order
+    for (int i = tid; i < TL.size; i += tc::THREADS) {
+        const int p = tc::tl_to_flat(i, C.tower, TL, L, O);
+        st_w[i] = p >= 0 ? E.params[p] : 0.f;
+        st_m[i] = p >= 0 ? E.exp_avg[p] : 0.f;
+        st_v[i] = p >= 0 ? E.exp_avg_sq[p] : 0.f;
+    }
+    __syncthreads();
+    tc::panel_w1_from_tl<KP>(C, st_w, TL, O);
+    tc::panel_w2_from_tl(C, st_w, TL);
+    __syncthreads();
+
+    tc::MbConst MK = tc::mb_const(E.stats, 0, A.normalize_adv);
+    for (int m = 0; m < n_mb; ++m) {
+        const float inv_cnt = MK.inv_b;
+        float* accb = E.acc + (size_t)(m % 3) * acc_floats;
+        // every CTA has passed barrier m - 1, i.e. nobody reads the accumulator of minibatch m - 2 any more
+        if (m >= 2 && slice_t)
+            __stcg(reinterpret_cast<float4*>(E.acc + (size_t)((m + 1) % 3) * acc_floats) + my_quad, make_float4(0.f, 0.f, 0.f, 0.f));
+        MR_TR(2);
+        const tc::TileAcc T = tc::tiles<KP>(C, A, S, MK, m, Q, O);
+        if (T.any) {
+            tc::stage_partial<KP>(C, T, MK, O, TL, stage);
+            umma::fence_proxy_async();   // the staged block (generic writes) -> the bulk reduction's reads
+            __syncthreads();
+            MR_TR(22);
+            if (tid == 0) {
+                bulk_reduce_add_f32(accb + (size_t)C.tower * TL.size, stage, (uint32_t)TL.size * 4u);
+                bulk_wait_all();
+            }
+        }
+        if (m + 1 < n_mb) MK = tc::mb_const(E.stats, m + 1, A.normalize_adv);   // loads land under the barrier
+        MR_TR(3);
+        grid_barrier(E.barrier, target, G);
+        MR_TR(4);
+        ++step;
+        b1pow *= (double)E.beta1;   // beta^step, carried from one pow() per launch
+        b2pow *= (double)E.beta2;
+
+        const float* src = accb;
+        if (E.X.world > 1) {
+            // one-shot all-reduce of this CTA's accumulator slice over NVLink peer memory: tagged 8-byte
+            // packets {seq, float} into every peer's inbox, summed in rank order (bit-identical everywhere)
+            if (slice_t) {
+                const float4 mine = __ldcg(reinterpret_cast<const float4*>(accb) + my_quad);
+                const float val[4] = {mine.x, mine.y, mine.z, mine.w};
+                const unsigned seq = E.seq0 + (unsigned)m + 1u;
+                const int slot = seq & 1u;
+                const size_t p = 4 * (size_t)my_quad;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned long long pkt = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(val[e]);
+                    for (int r = 0; r < E.X.world; ++r)
+                        if (r != E.X.rank)
+                            __stcg(E.X.peer_inbox[r] + ((size_t)slot * E.X.world + E.X.rank) * acc_floats + p + e, pkt);
+                }
+                // pull: the four packets of every peer, four peers per wave of 16-byte loads; payloads wait in
+                // shared memory.  A peer that never delivers (dead rank) ends the wait after ~4 s: the flag is
+                // raised and the epoch finishes on what arrived, so the GPU is released instead of hanging.
+                const unsigned long long* src0 = E.X.inbox + (size_t)slot * E.X.world * acc_floats + p;
+                unsigned pending = ((1u << E.X.world) - 1u) & ~(1u << E.X.rank);
+                long long t0 = 0;
+                unsigned spins = 0;
+                while (pending) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        ulonglong2 lo[4], hi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = 4 * half + k;
+                            if (pending >> r & 1u) {
+                                const unsigned long long* q = src0 + (size_t)r * acc_floats;
+                                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[k].x), "=l"(lo[k].y) : "l"(q) : "memory");
+                                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(hi[k].x), "=l"(hi[k].y) : "l"(q + 2) : "memory");
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = 4 * half + k;
+                            if ((pending >> r & 1u) && (unsigned)(lo[k].x >> 32) == seq && (unsigned)(lo[k].y >> 32) == seq &&
+                                (unsigned)(hi[k].x >> 32) == seq && (unsigned)(hi[k].y >> 32) == seq) {
+                                s_x[r * 32 + tid] = make_float4(__uint_as_float((unsigned)lo[k].x), __uint_as_float((unsigned)lo[k].y),
+                                                                __uint_as_float((unsigned)hi[k].x), __uint_as_float((unsigned)hi[k].y));
+                                pending &= ~(1u << r);
+                            }
+                        }
+                    }
+                    if (pending && (++spins & 0xFFFu) == 0) {
+                        long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 4000000000ll) {
+                            for (int r = 0; r < E.X.world; ++r)
+                                if (pending >> r & 1u) s_x[r * 32 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (E.X.err) *E.X.err = 1;
+                            pending = 0;
+                        }
+                    }
+                }
+                float tot[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int r = 0; r < E.X.world; ++r) {
+                    const float4 v = r == E.X.rank ? mine : s_x[r * 32 + tid];
+                    tot[0] += v.x; tot[1] += v.y; tot[2] += v.z; tot[3] += v.w;
+                }
+                __stcg(reinterpret_cast<float4*>(E.gsum) + my_quad, make_float4(tot[0], tot[1], tot[2], tot[3]));
+            }
+            MR_TR(5);
+            grid_barrier(E.barrier, target, G);
+            MR_TR(6);
+            src = E.gsum;
+        }
+
+        // ---- the whole reduced gradient: clip coefficient, then Adam on the own tower -------------------
+        tc::BlockRegs gOwn, gOth;
+        tc::load_block(src + (size_t)C.tower * TL.size, TL, gOwn);
+        tc::load_block(src + (size_t)(C.tower ^ 1) * TL.size, TL, gOth);
+        MR_TR(30);
+        double sq = tc::finish_block(gOwn, TL, C.tower == 0, E.G.ent_coef) + tc::finish_block(gOth, TL, C.tower != 0, E.G.ent_coef);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) s_sq[warp] = sq;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < tc::WARPS; ++w) tot += s_sq[w];
+        const float total_norm = (float)sqrt(tot);
+        tc::AdamK K;
+        K.coef = fminf(E.max_grad_norm / (total_norm + 1e-6f), 1.0f);
+        K.beta1 = E.beta1; K.beta2 = E.beta2; K.omb1 = 1.f - E.beta1; K.omb2 = 1.f - E.beta2;
+        K.neg_step_size = (float)(-(double)E.lr / (1.0 - b1pow));
+        K.bc2_sqrt = (float)sqrt(1.0 - b2pow);
+        K.eps = E.eps;
+        MR_TR(31);
+        tc::adam_block(C, gOwn, K, TL, st_w, st_m, st_v);
+        MR_TR(7);
+        // outputs of the API, off the other CTAs' critical path: statistics row (CTA 0), last gradient (CTAs 0, 1)
+        if (c < 2) {
+            const int q_st = (TL.st - TL.w1) >> 2;
+            if (E.info && c == 0) {
+                float* row = E.info + 8 * m;
+                if (tid == 0) { row[0] = total_norm; row[1] = K.coef; row[2] = (float)step; row[3] = 0.f; }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (tid + k * tc::THREADS == q_st) {   // policy: loss, clipped count, kl; value: squared error
+                        row[4] = gOwn.r[k].x * inv_cnt; row[5] = gOth.r[k].x * inv_cnt;
+                        row[6] = gOwn.r[k].y * inv_cnt; row[7] = gOwn.r[k].z * inv_cnt;
+                    }
+            }
+            if (m == n_mb - 1) {
+                const int sb = stat_base(O);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int idx = tid + k * tc::THREADS;
+                    const int p = (C.tower ? L.vw2 : L.pw2) + (idx >> 3) * HID + 8 * (idx & 7);
+                    const float4 a = gOwn.o[k][0], b = gOwn.o[k][1];
+                    const float v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) E.grad[p + e] = v8[e];
+                    const int qi = idx;
+                    const float r4[4] = {gOwn.r[k].x, gOwn.r[k].y, gOwn.r[k].z, gOwn.r[k].w};
+                    if (qi < ((TL.size - TL.w1) >> 2)) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int pf = tc::tl_to_flat(TL.w1 + 4 * qi + e, C.tower, TL, L, O);
+                            if (pf >= 0) E.grad[pf] = r4[e];
+                        }
+                        if (qi == q_st) {
+                            if (C.tower == 0) { E.grad[sb] = r4[0] * inv_cnt; E.grad[sb + 2] = r4[1] * inv_cnt; E.grad[sb + 3] = r4[2] * inv_cnt; }
+                            else E.grad[sb + 1] = r4[0] * inv_cnt;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // the tower's new fp32 values (other threads' Adam) -> W1 panel, head vectors
+        if (m + 1 < n_mb) tc::panel_w1_from_tl<KP>(C, st_w, TL, O);
+        MR_TR(37);
+    }
+    // tower state back to the flat arrays (every CTA of a tower holds the same bits: one writes)
+    if (c < 2) {
+        for (int i = tid; i < TL.size; i += tc::THREADS) {
+            const int p = tc::tl_to_flat(i, C.tower, TL, L, O);
+            if (p >= 0) {
+                E.params[p] = st_w[i];
+                E.exp_avg[p] = st_m[i];
+                E.exp_avg_sq[p] = st_v[i];
+            }
+        }
+    }
+    if (c == 0 && tid == 0) E.step[0] = step;
+    tc::teardown(C);
+}
+
 // The tensor-core kernels are the product path; MR_PPO_SIMT=1 selects the fp32 CUDA-core kernels
 // (kept as a cross-check of the tcgen05 path in the tests).
 static bool use_tc() {
@@ -1167,22 +1428,6 @@ static bool use_tc() {
         v = (e && e[0] == '1') ? 0 : 1;
     }
     return v == 1;
-}
-
-// library-owned scratch (one per device): the epoch's samples as buffer rows, for the tensor-core kernels
-static int rows_scratch(int dev, int64_t n, int32_t** out) {
-    static int32_t* buf[16] = {nullptr};
-    static int64_t cap[16] = {0};
-    MR_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
-    if (cap[dev] < n) {
-        if (buf[dev]) MR_CUDA(cudaFree(buf[dev]));
-        buf[dev] = nullptr;
-        cap[dev] = 0;
-        MR_CUDA(cudaMalloc(&buf[dev], (size_t)n * sizeof(int32_t)));
-        cap[dev] = n;
-    }
-    *out = buf[dev];
-    return MR_OK;
 }
 
 static size_t grad_smem_bytes(int O, int O_PAD) {
@@ -1199,12 +1444,8 @@ extern "C" {
 
 int mr_ppo_grad_stride(int obs_dim) { return grad_stride(obs_dim); }
 int mr_ppo_num_params(int obs_dim) { return make_layout(obs_dim).total; }
-int mr_ppo_max_parts(void) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-}
+int mr_ppo_max_parts(void) { return sm_count(); }
+int mr_ppo_epoch_scratch_floats(int obs_dim) { return 4 * 2 * tc::make_tl(obs_dim).size + 64; }
 
 int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, int64_t batch_size,
                      int64_t N, int64_t T, double* stats, void* stream) {
@@ -1239,10 +1480,10 @@ int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t*
 
 int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, const float* act,
                          const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
-                         int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
-                         float ent_coef, float vf_coef, int normalize_adv, float* partials, int* n_parts,
-                         void* stream) {
-    MR_REQUIRE(params && obs && act && old_logp && adv && ret && perm && mb_stats && partials,
+                         int32_t* rows, int64_t mb_size, const double* mb_stats, int64_t N, int64_t T,
+                         float clip_range, float ent_coef, float vf_coef, int normalize_adv, float* partials,
+                         int* n_parts, void* stream) {
+    MR_REQUIRE(params && obs && act && old_logp && adv && ret && perm && rows && mb_stats && partials,
                "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     MR_REQUIRE(mb_size > 0, "empty minibatch");
@@ -1250,26 +1491,19 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
                clip_range, ent_coef, vf_coef, normalize_adv, partials};
     const int o_pad = obs_dim <= 16 ? 16 : 32;
     const size_t smem = grad_smem_bytes(obs_dim, o_pad);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice once;
+    if (once.first()) {
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         MR_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_set = true;
     }
-    static int max_parts = 0;
-    if (!max_parts) max_parts = mr_ppo_max_parts();
+    const int max_parts = mr_ppo_max_parts();
     cudaStream_t s = (cudaStream_t)stream;
     int grid;
     if (use_tc()) {
         MR_REQUIRE(obs_dim < 32 && max_parts >= 2, "tensor-core path needs obs_dim < 32");
         MR_REQUIRE(N * T < (int64_t(1) << 31), "tensor-core path indexes samples with 32 bits");
-        int dev = 0;
-        MR_CUDA(cudaGetDevice(&dev));
-        int32_t* rows = nullptr;
-        int rc = rows_scratch(dev, mb_size, &rows);
-        if (rc != MR_OK) return rc;
         perm_to_rows_kernel<<<ceil_div(mb_size, 256), 256, 0, s>>>(perm, mb_size, N, T, rows);
         MR_CHECK_LAUNCH();
         A.rows = rows;
@@ -1292,12 +1526,12 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
 
 int mr_ppo_grad(const float* params, int obs_dim, const float* obs, const float* act,
                 const float* old_logp, const float* adv, const float* ret, const int64_t* perm,
-                int64_t mb_size, const double* mb_stats, int64_t N, int64_t T, float clip_range,
-                float ent_coef, float vf_coef, int normalize_adv, float rank_share,
+                int32_t* rows, int64_t mb_size, const double* mb_stats, int64_t N, int64_t T,
+                float clip_range, float ent_coef, float vf_coef, int normalize_adv, float rank_share,
                 float* partials, float* grad, void* stream) {
     MR_REQUIRE(grad, "NULL argument");
     int grid = 0;
-    int rc = mr_ppo_grad_partials(params, obs_dim, obs, act, old_logp, adv, ret, perm, mb_size, mb_stats,
+    int rc = mr_ppo_grad_partials(params, obs_dim, obs, act, old_logp, adv, ret, perm, rows, mb_size, mb_stats,
                                   N, T, clip_range, ent_coef, vf_coef, normalize_adv, partials, &grid, stream);
     if (rc != MR_OK) return rc;
     const int stride = grad_stride(obs_dim);
@@ -1319,17 +1553,17 @@ int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* 
 
 int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
                        const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
-                       const double* stats, int64_t N, int64_t T, float clip_range, float ent_coef,
-                       float vf_coef, int normalize_adv, float lr, float beta1, float beta2, float eps,
-                       float max_grad_norm, float* partials, float* grad, float* info, void* stream) {
+                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       int64_t batch_size, const double* stats, int64_t N, int64_t T, float clip_range,
+                       float ent_coef, float vf_coef, int normalize_adv, float lr, float beta1, float beta2,
+                       float eps, float max_grad_norm, float* partials, float* grad, float* info, void* stream) {
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     const int n_params = make_layout(obs_dim).total;
     const int64_t n_mb = (n_samples + batch_size - 1) / batch_size;
     for (int64_t mb = 0; mb < n_mb; ++mb) {
         const int64_t s0 = mb * batch_size;
         const int64_t sz = std::min(batch_size, n_samples - s0);
-        int rc = mr_ppo_grad(params, obs_dim, obs, act, old_logp, adv, ret, perm + s0, sz, stats + 3 * mb,
+        int rc = mr_ppo_grad(params, obs_dim, obs, act, old_logp, adv, ret, perm + s0, rows, sz, stats + 3 * mb,
                              N, T, clip_range, ent_coef, vf_coef, normalize_adv, 1.0f, partials, grad, stream);
         if (rc != MR_OK) return rc;
         rc = mr_adam_step(params, exp_avg, exp_avg_sq, grad, n_params, step, lr, beta1, beta2, eps,
@@ -1355,13 +1589,16 @@ int mr_trace_read(int cta, unsigned long long* out, int cap) {
 
 struct mr_xchg {
     int world, rank, device, n_cta;
-    int64_t stride;
-    void* base;            // local allocation: inbox floats then flags
+    int64_t stride;        // packets per (slot, rank): the larger of the two epoch kernels' vectors
+    void* base;            // local allocation: inbox packets, then the status word
     size_t bytes;
     void* peer_base[8];
     unsigned seq;          // exchange sequence number (host mirror)
 };
 
+static int64_t xchg_stride(int obs_dim) {
+    return std::max<int64_t>(grad_stride(obs_dim), 2 * (int64_t)tc::make_tl(obs_dim).size);
+}
 static size_t xchg_inbox_bytes(int world, int64_t stride) {
     return (size_t)2 * world * stride * sizeof(unsigned long long);
 }
@@ -1369,12 +1606,12 @@ static size_t xchg_inbox_bytes(int world, int64_t stride) {
 int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out) {
     MR_REQUIRE(out && h_handle_out, "NULL argument");
     MR_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad world/rank");
-    MR_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);   // the caller's current device is left as it was
     mr_xchg* x = new mr_xchg();
     x->world = world; x->rank = rank; x->device = device;
     x->n_cta = mr_ppo_max_parts();
-    x->stride = grad_stride(obs_dim);
-    x->bytes = xchg_inbox_bytes(world, x->stride);
+    x->stride = xchg_stride(obs_dim);
+    x->bytes = xchg_inbox_bytes(world, x->stride) + 256;
     x->seq = 0;
     for (int r = 0; r < 8; ++r) x->peer_base[r] = nullptr;
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
@@ -1391,7 +1628,7 @@ int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, 
 
 int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles) {
     MR_REQUIRE(x && h_all_handles, "NULL argument");
-    MR_CUDA(cudaSetDevice(x->device));
+    DeviceGuard guard(x->device);
     for (int r = 0; r < x->world; ++r) {
         if (r == x->rank) continue;
         cudaIpcMemHandle_t h;
@@ -1401,34 +1638,62 @@ int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles) {
     return MR_OK;
 }
 
+static int* xchg_status_word(mr_xchg* x) {
+    return reinterpret_cast<int*>(static_cast<char*>(x->base) + xchg_inbox_bytes(x->world, x->stride));
+}
+
+int mr_xchg_status(mr_xchg* x, int* timed_out) {
+    MR_REQUIRE(x && timed_out, "NULL argument");
+    DeviceGuard guard(x->device);
+    MR_CUDA(cudaMemcpy(timed_out, xchg_status_word(x), sizeof(int), cudaMemcpyDeviceToHost));
+    return MR_OK;
+}
+
 void mr_xchg_destroy(mr_xchg* x) {
     if (!x) return;
-    cudaSetDevice(x->device);
+    DeviceGuard guard(x->device);
     for (int r = 0; r < x->world; ++r)
         if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     cudaFree(x->base);
     delete x;
 }
 
+// MR_PPO_EPOCH=v1 selects the round-1 form of the tensor-core epoch kernel (148 partial vectors,
+// three grid barriers per minibatch; deterministic summation order) for A/B runs.
+static bool use_epoch_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MR_PPO_EPOCH");
+        v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
                        const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int64_t n_samples, int64_t batch_size,
-                       const double* stats, const float* rank_share, int64_t N, int64_t T,
+                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       int64_t batch_size, const double* stats, const float* rank_share, int64_t N, int64_t T,
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream) {
     MR_REQUIRE(params && exp_avg && exp_avg_sq && step && obs && act && old_logp && adv && ret && perm &&
-                   stats && partials && grad, "NULL argument");
+                   rows && stats && partials && grad, "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     cudaStream_t s = (cudaStream_t)stream;
-    int dev = 0;
-    MR_CUDA(cudaGetDevice(&dev));
-    static void* scratch[16] = {nullptr};
-    MR_REQUIRE(dev < 16, "device index out of range");
-    if (!scratch[dev]) MR_CUDA(cudaMalloc(&scratch[dev], 4096));
     const int n_cta = mr_ppo_max_parts();
-    MR_REQUIRE(n_cta <= 448, "too many SMs for the scratch layout");
+    const int stride = grad_stride(obs_dim);
+    const bool tcp = use_tc();
+    const bool v1 = tcp && use_epoch_v1();
+    const tc::TowerLayout TL = tc::make_tl(obs_dim);
+    const int acc_floats = 2 * TL.size;
+    MR_REQUIRE((int64_t)n_cta * stride >= mr_ppo_epoch_scratch_floats(obs_dim) && stride >= 2 * n_cta + 64,
+               "partials scratch too small for the epoch kernel");
+    // Everything the launch synchronises through lives in the CALLER's scratch (`partials`,
+    // (mr_ppo_max_parts() + 1) rows of grad_stride floats), so two updaters (different streams) never
+    // share a barrier word.  Current kernel: [3 accumulators | global sum | barrier word]; v1 / SIMT
+    // kernels: one partial vector per CTA in the first n_cta rows, [sq doubles | barrier word] in the
+    // extra row.
     EpochArgs E;
     E.G = GradArgs{params, obs, act, old_logp, adv, ret, perm, nullptr, 0, stats, N, T,
                    clip_range, ent_coef, vf_coef, normalize_adv, partials};
@@ -1436,48 +1701,59 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     E.params = params; E.exp_avg = exp_avg; E.exp_avg_sq = exp_avg_sq; E.step = step;
     E.lr = lr; E.beta1 = beta1; E.beta2 = beta2; E.eps = eps; E.max_grad_norm = max_grad_norm;
     E.grad = grad; E.info = info;
-    E.sq = reinterpret_cast<double*>(scratch[dev]);
-    E.barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch[dev]) + 3840);
-    MR_CUDA(cudaMemsetAsync(E.barrier, 0, sizeof(unsigned), s));
-    E.X.world = 1; E.X.rank = 0; E.X.inbox = nullptr;
+    E.acc = nullptr; E.gsum = nullptr; E.sq = nullptr;
+    if (tcp && !v1) {
+        E.acc = partials;
+        E.gsum = partials + 3 * (size_t)acc_floats;
+        E.barrier = reinterpret_cast<unsigned*>(partials + 4 * (size_t)acc_floats);
+        MR_CUDA(cudaMemsetAsync(partials, 0, (4 * (size_t)acc_floats + 16) * sizeof(float), s));
+        MR_CUDA(cudaMemsetAsync(grad, 0, (size_t)stride * sizeof(float), s));
+        MR_REQUIRE((acc_floats / 4 + n_cta - 1) / n_cta <= 32, "accumulator slice per CTA too wide");
+    } else {
+        float* tail = partials + (size_t)n_cta * stride;   // stride is a multiple of 4: 16-byte aligned
+        E.sq = reinterpret_cast<double*>(tail);
+        E.barrier = reinterpret_cast<unsigned*>(tail + 2 * (size_t)n_cta + 16);
+        MR_CUDA(cudaMemsetAsync(E.barrier, 0, sizeof(unsigned), s));
+    }
+    E.X.world = 1; E.X.rank = 0; E.X.inbox = nullptr; E.X.err = nullptr;
     E.seq0 = 0;
     const int64_t n_mb = (n_samples + batch_size - 1) / batch_size;
     if (xchg && xchg->world > 1) {
-        MR_REQUIRE(xchg->stride == grad_stride(obs_dim) && xchg->n_cta == n_cta, "exchange buffer mismatch");
+        MR_REQUIRE(xchg->stride == xchg_stride(obs_dim) && xchg->n_cta == n_cta, "exchange buffer mismatch");
         E.X.world = xchg->world; E.X.rank = xchg->rank;
         for (int r = 0; r < xchg->world; ++r)
             E.X.peer_inbox[r] = reinterpret_cast<unsigned long long*>(xchg->peer_base[r]);
         E.X.inbox = E.X.peer_inbox[xchg->rank];
+        E.X.err = xchg_status_word(xchg);
         E.seq0 = xchg->seq;
         xchg->seq += (unsigned)n_mb;
     }
-    const bool tcp = use_tc();
     MR_REQUIRE(!tcp || ((n_cta & 1) == 0 && obs_dim < 32), "tensor-core path needs an even CTA count and obs_dim < 32");
     const int o_pad = tcp ? (obs_dim + 1 <= 16 ? 16 : 32) : (obs_dim <= 16 ? 16 : 32);
-    const size_t smem = tcp ? (size_t)tc::SMEM_BYTES : grad_smem_bytes(obs_dim, o_pad);
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t smem_epoch = (size_t)tc::SMEM_BYTES + 3 * (size_t)tc::make_tl(MAX_OBS - 1).size * sizeof(float);
+    const size_t smem = tcp ? (v1 ? (size_t)tc::SMEM_BYTES : (size_t)tc::SMEM_BYTES + 3 * (size_t)TL.size * sizeof(float))
+                            : grad_smem_bytes(obs_dim, o_pad);
+    static OncePerDevice once;
+    if (once.first()) {
         MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MR_CUDA(cudaFuncSetAttribute(ppo_epoch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_set = true;
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_v1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_v1_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_epoch));
+        MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_epoch));
     }
     if (tcp) {
         MR_REQUIRE(n_samples < (int64_t(1) << 31) && N * T < (int64_t(1) << 31),
                    "tensor-core path indexes samples with 32 bits");
-        int32_t* rows = nullptr;
-        int rc = rows_scratch(dev, n_samples, &rows);
-        if (rc != MR_OK) return rc;
         perm_to_rows_kernel<<<ceil_div(n_samples, 256), 256, 0, s>>>(perm, n_samples, N, T, rows);
         MR_CHECK_LAUNCH();
         E.G.rows = rows;
-        const int stride = grad_stride(obs_dim);
-        MR_REQUIRE((((stride + n_cta - 1) / n_cta + 3) >> 2) <= 32, "gradient slice per CTA too wide");
+        if (v1) MR_REQUIRE((((stride + n_cta - 1) / n_cta + 3) >> 2) <= 32, "gradient slice per CTA too wide");
     }
     int O = obs_dim;
     void* args[] = {&E, &O};
-    const void* fn = tcp ? (o_pad == 16 ? (const void*)ppo_epoch_tc_kernel<16> : (const void*)ppo_epoch_tc_kernel<32>)
+    const void* fn = tcp ? (v1 ? (o_pad == 16 ? (const void*)ppo_epoch_tc_v1_kernel<16> : (const void*)ppo_epoch_tc_v1_kernel<32>)
+                               : (o_pad == 16 ? (const void*)ppo_epoch_tc_kernel<16> : (const void*)ppo_epoch_tc_kernel<32>))
                          : (o_pad == 16 ? (const void*)ppo_epoch_kernel<16> : (const void*)ppo_epoch_kernel<32>);
     MR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(tcp ? tc::THREADS : PG_THREADS), args, smem, s));
     mr::count_launch();

@@ -181,12 +181,10 @@ using namespace mr;
 template <int RO_WARPS, int RO_E>
 static int launch_rollout_cfg(const RolloutArgs& A, int64_t n_envs, cudaStream_t stream) {
     const size_t smem = (smem_w_floats(A.O) + RO_WARPS * (MAX_OBS * RO_E + 128 * RO_E)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice once;
+    if (once.first())
         MR_CUDA(cudaFuncSetAttribute(point_rollout_kernel<RO_WARPS, RO_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      100 * 1024));
-        attr_set = true;
-    }
     const int64_t warps = (n_envs + RO_E - 1) / RO_E;
     const int blocks = (int)((warps + RO_WARPS - 1) / RO_WARPS);
     point_rollout_kernel<RO_WARPS, RO_E><<<blocks, RO_WARPS * 32, smem, stream>>>(A);
@@ -297,7 +295,7 @@ extern "C" int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, f
     // term_obs O f32, ep_ret f64, ep_len i32, act_scratch 2 f32
     const size_t per_env = 4 + 4 + 8 + 1 + 1 + (size_t)O * 4 + 8 + 4 + 8 + 16;
     if (!env->scratch) {
-        MR_CUDA(cudaSetDevice(env->device));
+        DeviceGuard guard(env->device);
         MR_CUDA(cudaMalloc(&env->scratch, per_env * N + 4096));
         MR_CUDA(cudaMemsetAsync(env->scratch, 0, per_env * N + 4096, s));
     }

@@ -31,8 +31,17 @@ class PpoUpdater:
         self.exp_avg = torch.zeros(self.n_params, **f32)
         self.exp_avg_sq = torch.zeros(self.n_params, **f32)
         self.step = torch.zeros(2, dtype=torch.int64, device=device)  # [count, kernel ticket]
-        self.partials = torch.zeros((self.max_parts, self.stride), **f32)
+        # caller-owned scratch of the update kernels (include/mobrob_b200.h): one partial vector per
+        # CTA plus one row; the fused epoch kernel keeps its accumulators and barrier word in it
+        self.partials = torch.zeros((self.max_parts + 1, self.stride), **f32)
         self.grad = torch.zeros(self.stride, **f32)
+        self._rows = torch.empty(0, dtype=torch.int32, device=device)
+
+    def rows(self, n: int) -> torch.Tensor:
+        """int32 scratch for the samples as buffer rows (owned here, not by the library)."""
+        if self._rows.numel() < n:
+            self._rows = torch.empty(n, dtype=torch.int32, device=self.device)
+        return self._rows
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -51,9 +60,10 @@ class PpoUpdater:
         _lib.check(self.lib.mr_ppo_grad(
             self.params.data_ptr(), self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(),
             buf["log_probs"].data_ptr(), buf["advantages"].data_ptr(), buf["returns"].data_ptr(),
-            perm_slice.data_ptr(), perm_slice.numel(), mb_stats.data_ptr(), N, T,
-            self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
-            rank_share, self.partials.data_ptr(), self.grad.data_ptr(), self._stream()))
+            perm_slice.data_ptr(), self.rows(perm_slice.numel()).data_ptr(), perm_slice.numel(),
+            mb_stats.data_ptr(), N, T, self.clip_range, self.ent_coef, self.vf_coef,
+            int(self.normalize_advantage), rank_share, self.partials.data_ptr(), self.grad.data_ptr(),
+            self._stream()))
         return self.grad
 
     def compute_partials(self, buf: dict, perm_slice: torch.Tensor, mb_stats: torch.Tensor, N: int, T: int):
@@ -61,9 +71,9 @@ class PpoUpdater:
         _lib.check(self.lib.mr_ppo_grad_partials(
             self.params.data_ptr(), self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(),
             buf["log_probs"].data_ptr(), buf["advantages"].data_ptr(), buf["returns"].data_ptr(),
-            perm_slice.data_ptr(), perm_slice.numel(), mb_stats.data_ptr(), N, T,
-            self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
-            self.partials.data_ptr(), None, self._stream()))
+            perm_slice.data_ptr(), self.rows(perm_slice.numel()).data_ptr(), perm_slice.numel(),
+            mb_stats.data_ptr(), N, T, self.clip_range, self.ent_coef, self.vf_coef,
+            int(self.normalize_advantage), self.partials.data_ptr(), None, self._stream()))
 
     def adam_step(self, info: torch.Tensor | None = None):
         _lib.check(self.lib.mr_adam_step(
@@ -78,7 +88,8 @@ class PpoUpdater:
         _lib.check(self.lib.mr_ppo_train_epoch(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
             self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
-            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(), perm.numel(), batch_size,
+            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(),
+            self.rows(min(perm.numel(), batch_size)).data_ptr(), perm.numel(), batch_size,
             stats.data_ptr(), N, T, self.clip_range, self.ent_coef, self.vf_coef, int(self.normalize_advantage),
             self.lr, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, self.partials.data_ptr(),
             self.grad.data_ptr(), None if info is None else info.data_ptr(), self._stream()))
@@ -91,7 +102,8 @@ class PpoUpdater:
         _lib.check(self.lib.mr_ppo_epoch_fused(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
             self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
-            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(), perm.numel(), batch_size,
+            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(),
+            self.rows(perm.numel()).data_ptr(), perm.numel(), batch_size,
             stats.data_ptr(), None if rank_share is None else rank_share.data_ptr(), N, T, self.clip_range,
             self.ent_coef, self.vf_coef, int(self.normalize_advantage), self.lr, self.betas[0], self.betas[1],
             self.eps, self.max_grad_norm, self.partials.data_ptr(), self.grad.data_ptr(),
@@ -119,6 +131,14 @@ class PeerExchange:
         flat = np.frombuffer(b"".join(allh), dtype=np.uint8).copy()
         _lib.check(self.lib.mr_xchg_connect(self.handle, flat.ctypes.data))
         dist.barrier()
+
+    def timed_out(self) -> bool:
+        """True if an in-kernel exchange gave up waiting for a peer (synchronises the device)."""
+        import ctypes
+
+        flag = ctypes.c_int(0)
+        _lib.check(self.lib.mr_xchg_status(self.handle, ctypes.byref(flag)))
+        return bool(flag.value)
 
     def close(self):
         if getattr(self, "handle", None) is not None:

@@ -15,9 +15,7 @@ from mobrob_b200 import build as B
 TRACE_LIB = os.path.join(B.LIB_DIR, "libmobrob_b200_trace.so")
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
-    os.makedirs(B.LIB_DIR, exist_ok=True)
-    subprocess.check_call(["nvcc", *B.NVCC_FLAGS, "-DMR_TRACE", "-o", TRACE_LIB, *B.sources()], cwd=B.CSRC)
-    print(TRACE_LIB)
+    print(B.build(lib_path=TRACE_LIB, defines=("-DMR_TRACE",)))
     sys.exit(0)
 
 os.environ["MR_LIB_PATH"] = TRACE_LIB
@@ -45,10 +43,10 @@ for cta in (0, 1):
 model.collect_rollouts()
 model.train()
 torch.cuda.synchronize()
-NAMES = {1: "mb start", 2: "staged", 3: "minibatch done", 4: "barrier A passed", 5: "slice reduced", 6: "barrier B passed",
-         7: "adam done", 8: "barrier C passed", 10: "tile start", 11: "gathered+sync", 12: "Z1 done", 13: "H1 stored+sync",
+NAMES = {1: "mb start", 2: "mb start", 3: "partial reduced", 4: "barrier A passed", 5: "slice exchanged", 6: "barrier B passed",
+         7: "adam done", 8: "barrier C passed", 22: "partial staged", 10: "tile start", 11: "gathered+sync", 12: "Z1 done", 13: "H1 stored+sync",
          14: "Z2 done", 15: "heads/dZ2 stored+sync", 16: "dH done", 17: "dZ1 computed", 18: "dW2 done",
-         19: "dZ1 stored+sync", 20: "tiles issued", 21: "dW1 done", 30: "partials loaded", 31: "partials synced",
+         19: "dZ1 stored+sync", 20: "tiles issued", 21: "dW1 done", 30: "gradient loaded", 31: "norm known",
          32: "slice summed", 33: "norm known", 34: "adam ctx", 35: "adam pass 1", 36: "adam pass 1 synced",
          37: "restaged"}
 for cta in (0, 1):
@@ -57,7 +55,7 @@ for cta in (0, 1):
     ts = (buf[:n] & np.uint64((1 << 56) - 1)).astype(np.int64)
     print(f"== CTA {cta}: {n} marks")
     # first 2 minibatches verbatim, then per-phase averages
-    starts = [i for i in range(n) if ids[i] == 1]
+    starts = [i for i in range(n) if ids[i] == 2]
     for i in range(starts[1] if len(starts) > 1 else 0, starts[3] if len(starts) > 3 else n):
         print(f"   {NAMES.get(ids[i], ids[i]):28s} +{(ts[i] - ts[i - 1]) if i else 0:7d} ns")
     agg = {}
