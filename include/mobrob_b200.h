@@ -159,8 +159,9 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
 /* clip_grad_norm_(max_grad_norm) then torch.optim.Adam.step (eps as given; SB3 uses 1e-5).
  * step: device int64[2]: [0] = Adam step count (state["step"]), incremented; [1] = launch-internal
  * ticket that must start at 0.  info [8] out (may be NULL):
- * total grad norm, clip coefficient, step, 0, then grad's stats tail (policy_loss, value_loss,
- * clip_fraction, approx_kl) so that logging needs no extra copy. */
+ * total grad norm, clip coefficient, step, the minibatch's entropy_loss (from the log_std it was
+ * evaluated with), then grad's stats tail (policy_loss, value_loss, clip_fraction, approx_kl) so that
+ * logging needs no extra copy. */
 int mr_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grad, int n_params,
                  int64_t* step, float lr, float beta1, float beta2, float eps, float max_grad_norm,
                  float* info, void* stream);
@@ -184,6 +185,15 @@ int mr_rollout(mr_env* env, const float* params, int64_t T, float* last_obs, flo
                uint64_t noise_offset, int64_t env_offset, double gamma, double* ep_r,
                int32_t* ep_l, unsigned long long* ep_count, int ring_cap, void* stream);
 
+/* What [SB3] PPO.train logs after its epochs, in one launch and without a host round trip.
+ * info [n_rows][8]: the info rows of every minibatch of the update; values / returns [n] the flat buffer;
+ * params: the flat parameter vector after the update.  out [12] f32: [0:4] mean policy_gradient_loss,
+ * value_loss, clip_fraction, approx_kl; [4:6] the last minibatch's policy and value loss; [6]
+ * explained_variance(values, returns) (nan if var(returns) == 0); [7:9] log_std; [9] mean entropy_loss;
+ * [10] the last minibatch's entropy_loss; [11] n_rows.  scratch: 8 doubles, zero before the first call. */
+int mr_ppo_train_summary(const float* info, int n_rows, const float* values, const float* returns, int64_t n,
+                         const float* params, float* out, double* scratch, void* stream);
+
 /* One epoch of PPO.train on one GPU: for every minibatch of perm, mr_ppo_grad then mr_adam_step,
  * launched back to back from C (no host round trip between minibatches).  stats [n_mb][3] from
  * mr_ppo_adv_stats; info [n_mb][8] receives mr_adam_step's info rows (may be NULL). */
@@ -202,8 +212,8 @@ int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t
  * memory: each CTA pushes its slice of the reduced gradient into every peer's inbox as tagged
  * packets and sums the ranks' slices in rank order (parameters stay bit-identical on all ranks).
  * A peer that stops delivering ends the wait after ~4 s and raises the flag mr_xchg_status reads.
- * rows [n_samples] int32 caller-owned scratch.  rank_share [n_mb] device floats (local / global
- * minibatch count) or NULL. */
+ * rows [n_samples] int32 caller-owned scratch.  stats: the GLOBAL minibatches' sums (all-reduced by the
+ * host when several ranks train), which is all the kernel needs to know about the other ranks' shares. */
 typedef struct mr_xchg mr_xchg;
 /* Allocate this rank's inbox; h_handle_out receives its 64-byte CUDA IPC handle. */
 int mr_xchg_create(int world, int rank, int device, int obs_dim, mr_xchg** out, uint8_t* h_handle_out);
@@ -215,7 +225,7 @@ int mr_xchg_status(mr_xchg* x, int* timed_out);
 int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
                        const float* obs, const float* act, const float* old_logp, const float* adv,
                        const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
-                       int64_t batch_size, const double* stats, const float* rank_share, int64_t N, int64_t T,
+                       int64_t batch_size, const double* stats, int64_t N, int64_t T,
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream);

@@ -96,6 +96,9 @@ class PPO:
             arch = (policy_kwargs or {}).get("net_arch")
             if arch not in (None, dict(pi=[64, 64], vf=[64, 64])):
                 raise NotImplementedError("kernels are specialised for net_arch pi=[64,64], vf=[64,64]")
+        # SB3 schedules: callables of the remaining progress (1 -> 0), evaluated before every update
+        self._lr_schedule = learning_rate if callable(learning_rate) else None
+        self._clip_schedule = clip_range if callable(clip_range) else None
         if callable(learning_rate):
             learning_rate = float(learning_rate(1.0))
         if callable(clip_range):
@@ -118,7 +121,10 @@ class PPO:
         self._feeder = None
         self._train_count = 0
         self._train_stats = None
+        self._train_meta = None
+        self._snap_meta = None
         self._snap = None
+        self._current_progress_remaining = 1.0
         self._stats_window_size = stats_window_size
         self.num_timesteps = 0
         self._total_timesteps = 0
@@ -184,10 +190,29 @@ class PPO:
     def get_env(self):
         return self.env
 
-    def set_env(self, env):
+    def set_env(self, env, force_reset=True):
+        """SB3's ``m = PPO.load(path); m.set_env(env); m.learn(...)``: attach a GpuVecEnv, (re)allocate the
+        rollout buffers on ITS device and keep the loaded parameters and Adam state."""
+        if not isinstance(env, GpuVecEnv):
+            raise TypeError("mobrob_b200.PPO trains on a GpuVecEnv (the envs live in HBM)")
+        if self.policy is not None and env.obs_dim != self.updater.obs_dim:
+            raise ValueError(f"observation dimension {env.obs_dim} does not match the policy's {self.updater.obs_dim}")
+        old = self.updater if self.policy is not None else None
         self.env = env
         self.n_envs = env.num_envs
-        self._setup_model_buffers_only = True
+        self.observation_space, self.action_space = env.observation_space, env.action_space
+        seed, self.seed = self.seed, None   # set_random_seed / orthogonal init belong to construction only
+        self._setup_model()
+        self.seed = seed
+        if old is not None:
+            up = self.updater
+            up.params.copy_(old.params.to(up.device))
+            up.exp_avg.copy_(old.exp_avg.to(up.device))
+            up.exp_avg_sq.copy_(old.exp_avg_sq.to(up.device))
+            up.step.copy_(old.step.to(up.device))
+            up.lr, up.betas, up.eps = old.lr, old.betas, old.eps
+        self._xchg = None
+        self._log = None
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -239,6 +264,7 @@ class PPO:
         sn["l"].copy_(self.ep_l[idx], non_blocking=True)
         if self._train_stats is not None:
             sn["train"].copy_(self._train_stats, non_blocking=True)
+            self._snap_meta = self._train_meta
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         return ev
@@ -309,7 +335,15 @@ class PPO:
         B = self.batch_size
         n_mb = (n + B - 1) // B
         d = _dist()
-        log = torch.zeros((self.n_epochs * n_mb, 8), dtype=torch.float32, device=self.device)
+        self._update_schedules()
+        rows = self.n_epochs * n_mb
+        if getattr(self, "_log", None) is None or self._log.shape[0] != rows:
+            # per-minibatch info rows (every row is written by the kernels), the 12 logger inputs of the
+            # update and the summary kernel's scratch: allocated once, no per-iteration torch launches
+            self._log = torch.zeros((rows, 8), dtype=torch.float32, device=self.device)
+            self._train_stats_buf = torch.zeros(12, dtype=torch.float32, device=self.device)
+            self._sum_scratch = torch.zeros(8, dtype=torch.float64, device=self.device)
+        log = self._log
         k = 0
         for epoch in range(self.n_epochs):
             perm = perms[epoch] if perms is not None else self._permutation(n, epoch)
@@ -320,13 +354,12 @@ class PPO:
             share = None
             if d is not None:
                 stats, share = sharding.allreduce_adv_stats(stats)
-                share = share.to(torch.float32).contiguous()
             if self.update_mode == "fused":      # one cooperative launch per epoch (+ NVLink all-reduce)
                 if d is not None and self._xchg is None:
                     from .updater import PeerExchange
 
                     self._xchg = PeerExchange(up.obs_dim, self.device)
-                up.train_epoch_fused(b, perm, stats, B, N, T, log[k:k + n_mb], share, self._xchg)
+                up.train_epoch_fused(b, perm, stats, B, N, T, log[k:k + n_mb], self._xchg)
                 k += n_mb
             elif d is None:                      # 3 launches per minibatch, looped in C
                 up.train_epoch(b, perm, stats, B, N, T, log[k:k + n_mb])
@@ -344,38 +377,44 @@ class PPO:
         self._train_count += 1
         self._n_updates += self.n_epochs
         self._train_log = (log[:, 4:], log[:, :4])
-        # logger inputs, computed on the device behind the last epoch (read one iteration later):
-        # [0:4] mean policy_loss / value_loss / clip_fraction / approx_kl, [4:6] last minibatch's
-        # policy and value loss, [6] explained variance of the buffer this update trained on,
-        # [7:9] log_std after the update
-        tails = log[:, 4:]
-        y_pred, y_true = b["values"].flatten(), b["returns"].flatten()
-        var_y = torch.var(y_true)
-        ev = torch.where(var_y == 0, torch.full_like(var_y, float("nan")), 1 - torch.var(y_true - y_pred) / var_y)
-        st = torch.zeros(12, dtype=torch.float32, device=self.device)
-        st[0:4] = tails.mean(dim=0)
-        st[4:6] = tails[-1, 0:2]
-        st[6] = ev
-        st[7:9] = self.policy.state_dict()["log_std"]
-        self._train_stats = st
+        # logger inputs of this update (mr_ppo_train_summary), read one iteration later -- SB3 records
+        # train/* inside train() and dumps them with the NEXT iteration's rollout statistics
+        _lib.check(self.lib.mr_ppo_train_summary(log.data_ptr(), rows, b["values"].data_ptr(), b["returns"].data_ptr(),
+                                                 n, up.params.data_ptr(), self._train_stats_buf.data_ptr(),
+                                                 self._sum_scratch.data_ptr(), self._stream()))
+        self._train_stats = self._train_stats_buf
+        self._train_meta = dict(n_updates=self._n_updates, clip_range=self.clip_range, learning_rate=up.lr)
+
+    def _update_schedules(self):
+        """SB3's _update_learning_rate / clip_range(progress): constant values or callables of the
+        remaining progress (1 -> 0); both are per-launch kernel arguments."""
+        progress = 1.0   # _update_current_progress_remaining: 1 - num_timesteps / total_timesteps
+        if self._total_timesteps:
+            progress = 1.0 - float(self.num_timesteps) / float(self._total_timesteps)
+        self._current_progress_remaining = progress
+        if self._lr_schedule is not None:
+            self.learning_rate = float(self._lr_schedule(progress))
+        if self._clip_schedule is not None:
+            self.clip_range = float(self._clip_schedule(progress))
+        self.updater.lr = self.learning_rate
+        self.updater.clip_range = self.clip_range
 
     def _log_train(self):
         """train/* keys of SB3's PPO.train, from the statistics snapshot of the previous update."""
         t = self._snap["train"].numpy()
-        ls_h = t[7:9].astype(np.float64)
-        ent = -float((0.5 + 0.5 * np.log(2 * np.pi) + ls_h).sum())
+        meta = self._snap_meta
         lg = self.logger
-        lg.record("train/entropy_loss", ent)
+        lg.record("train/entropy_loss", float(t[9]))
         lg.record("train/policy_gradient_loss", float(t[0]))
         lg.record("train/value_loss", float(t[1]))
         lg.record("train/approx_kl", float(t[3]))
         lg.record("train/clip_fraction", float(t[2]))
-        lg.record("train/loss", float(t[4] + self.ent_coef * ent + self.vf_coef * t[5]))
+        lg.record("train/loss", float(t[4] + self.ent_coef * t[10] + self.vf_coef * t[5]))
         lg.record("train/explained_variance", float(t[6]))
-        lg.record("train/std", float(np.exp(ls_h).mean()))
-        lg.record("train/n_updates", self._n_updates)
-        lg.record("train/clip_range", self.clip_range)
-        lg.record("train/learning_rate", self.learning_rate)
+        lg.record("train/std", float(np.exp(t[7:9].astype(np.float32)).mean()))
+        lg.record("train/n_updates", meta["n_updates"])
+        lg.record("train/clip_range", meta["clip_range"])
+        lg.record("train/learning_rate", meta["learning_rate"])
 
     # -- learn ----------------------------------------------------------------------------------------
     def learn(self, total_timesteps, callback=None, log_interval=1, tb_log_name="PPO",
@@ -478,7 +517,9 @@ class PPO:
             "verbose": self.verbose, "policy_kwargs": {},
             "num_timesteps": self.num_timesteps, "_total_timesteps": self._total_timesteps,
             "_num_timesteps_at_start": self._num_timesteps_at_start, "seed": self.seed,
-            "action_noise": None, "start_time": self.start_time, "learning_rate": lr,
+            "action_noise": None, "start_time": self.start_time,
+            "learning_rate": (lr if self._lr_schedule is None else
+                              {":type:": "<class 'function'>", ":serialized:": ser(self._lr_schedule), "value": lr}),
             "tensorboard_log": self.tensorboard_log,
             "_last_obs": {":type:": "<class 'numpy.ndarray'>", ":serialized:": ser(last_obs)},
             "_last_episode_starts": {":type:": "<class 'numpy.ndarray'>", ":serialized:": ser(starts)},
@@ -491,11 +532,13 @@ class PPO:
             "_n_updates": self._n_updates, "n_steps": self.n_steps, "gamma": self.gamma,
             "gae_lambda": self.gae_lambda, "ent_coef": self.ent_coef, "vf_coef": self.vf_coef,
             "max_grad_norm": self.max_grad_norm, "batch_size": self.batch_size, "n_epochs": self.n_epochs,
-            "clip_range": {":type:": "<class 'function'>", ":serialized:": ser(_Constant(cr)), "value": cr},
+            "clip_range": {":type:": "<class 'function'>", ":serialized:": ser(self._clip_schedule or _Constant(cr)),
+                           "value": cr},
             "clip_range_vf": None, "normalize_advantage": self.normalize_advantage, "target_kl": None,
             "observation_space": space(self.observation_space), "action_space": space(self.action_space),
             "n_envs": self.n_envs,
-            "lr_schedule": {":type:": "<class 'function'>", ":serialized:": ser(_Constant(lr)), "value": lr},
+            "lr_schedule": {":type:": "<class 'function'>", ":serialized:": ser(self._lr_schedule or _Constant(lr)),
+                            "value": lr},
         }
 
     def save(self, path):
@@ -547,10 +590,8 @@ class PPO:
         plain = ("n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "ent_coef", "vf_coef",
                  "max_grad_norm", "normalize_advantage", "verbose", "seed")
         ctor = {k: data[k] for k in plain if k in data}
-        lr = data.get("learning_rate", 3e-4)
-        ctor["learning_rate"] = lr if isinstance(lr, (int, float)) else 3e-4
-        cr = data.get("clip_range", {})
-        ctor["clip_range"] = cr.get("value", 0.2) if isinstance(cr, dict) else float(cr)
+        ctor["learning_rate"] = _stored_schedule(data.get("learning_rate", 3e-4), "learning_rate")
+        ctor["clip_range"] = _stored_schedule(data.get("clip_range", 0.2), "clip_range")
         ctor.update(kwargs)
         model = cls("MlpPolicy", env, _init_setup_model=False, **ctor)
         for k in ("num_timesteps", "_total_timesteps", "_num_timesteps_at_start", "_n_updates", "_episode_num"):
@@ -583,6 +624,30 @@ class PPO:
             up.exp_avg_sq.copy_(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(st))]))
             up.step[0] = int(st[0]["step"])
         return model
+
+
+def _stored_schedule(entry, what):
+    """A hyper-parameter as SB3 stores it in the zip's ``data``: a number, or a pickled schedule
+    ({":serialized:": base64 cloudpickle}) -- constant_fn for the shipped zips.  A stored callable is
+    returned as a callable (PPO evaluates it before every update); nothing is silently replaced."""
+    if isinstance(entry, (int, float)):
+        return float(entry)
+    if isinstance(entry, dict):
+        blob = entry.get(":serialized:")
+        if blob:
+            try:
+                import cloudpickle
+
+                fn = cloudpickle.loads(base64.b64decode(blob))
+                if callable(fn):
+                    if isinstance(fn, _Constant):
+                        return fn.val
+                    return fn
+            except Exception:
+                pass
+        if isinstance(entry.get("value"), (int, float)):
+            return float(entry["value"])
+    raise NotImplementedError(f"cannot restore the stored {what} schedule: {str(entry)[:120]}")
 
 
 class _Constant:

@@ -95,16 +95,15 @@ class PpoUpdater:
             self.grad.data_ptr(), None if info is None else info.data_ptr(), self._stream()))
 
     def train_epoch_fused(self, buf: dict, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int,
-                          T: int, info: torch.Tensor | None = None, rank_share: torch.Tensor | None = None,
-                          xchg=None):
+                          T: int, info: torch.Tensor | None = None, xchg=None):
         """One cooperative launch for the whole epoch; xchg (PeerExchange) adds the in-kernel
-        NVLink all-reduce of the gradient."""
+        NVLink all-reduce of the gradient (stats must then be the all-reduced, global sums)."""
         _lib.check(self.lib.mr_ppo_epoch_fused(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
             self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
             buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(),
             self.rows(perm.numel()).data_ptr(), perm.numel(), batch_size,
-            stats.data_ptr(), None if rank_share is None else rank_share.data_ptr(), N, T, self.clip_range,
+            stats.data_ptr(), N, T, self.clip_range,
             self.ent_coef, self.vf_coef, int(self.normalize_advantage), self.lr, self.betas[0], self.betas[1],
             self.eps, self.max_grad_norm, self.partials.data_ptr(), self.grad.data_ptr(),
             None if info is None else info.data_ptr(), None if xchg is None else xchg.handle, self._stream()))

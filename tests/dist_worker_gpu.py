@@ -55,7 +55,7 @@ def main():
             stats, share = sharding.allreduce_adv_stats(stats)
             share = share.to(torch.float32).contiguous()
             if mode == "fused":
-                up.train_epoch_fused(mine, perm, stats, b_local, n_local, T, info, share, xchg)
+                up.train_epoch_fused(mine, perm, stats, b_local, n_local, T, info, xchg)
             else:
                 sh = share.cpu().tolist()
                 for m in range(n_mb):

@@ -13,6 +13,11 @@ Outputs:
   * ``kat2.json``                 mu / V of the shipped policy on _last_obs (torch CPU fp32)
   * ``policies/{env}-ppo.zip``    byte copy of the shipped artefact (load/save tests)
   * ``ref_rng.json``              a few draws of the reference RNG streams (numpy)
+  * ``examples/{train,control}.py``  byte copies of the reference's example scripts: INPUTS of
+                                  tests/test_examples_gpu.py, which runs them unchanged through
+                                  shims/ (they are fixtures, not product code -- nothing imports them)
+  * ``kat4_ep_info.json``         the 100 most recent training episodes (r, l) stored in the shipped
+                                  zips (``data:ep_info_buffer``, written by the real SB3 + MuJoCo run)
 """
 import base64
 import io
@@ -64,6 +69,24 @@ def main():
         print(env, last_obs.shape, mu, v)
     with open(os.path.join(HERE, "kat2.json"), "w") as f:
         json.dump(kat2, f, indent=1)
+
+    # the example scripts, byte for byte
+    os.makedirs(os.path.join(HERE, "examples"), exist_ok=True)
+    for name in ("train.py", "control.py"):
+        shutil.copyfile(f"{REF}/examples/{name}", os.path.join(HERE, "examples", name))
+
+    # KAT-4: Monitor's episode records of the reference's own training run
+    kat4 = {}
+    for env in ("point", "car"):
+        data = json.loads(zipfile.ZipFile(f"{REF}/data/policies/{env}-ppo.zip").read("data"))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            eps = pickle.loads(base64.b64decode(data["ep_info_buffer"][":serialized:"]))
+        kat4[env] = {"r": [float(e["r"]) for e in eps], "l": [int(e["l"]) for e in eps],
+                     "n_steps": data["n_steps"], "n_envs": data["n_envs"], "num_timesteps": data["num_timesteps"]}
+        print(env, "ep_info_buffer:", len(eps), "episodes, mean length", np.mean(kat4[env]["l"]))
+    with open(os.path.join(HERE, "kat4_ep_info.json"), "w") as f:
+        json.dump(kat4, f)
 
     # Reference RNG streams (numpy is the arithmetic; this freezes our reading of the call order)
     from oracle import ref_rng

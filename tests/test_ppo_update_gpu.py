@@ -53,8 +53,20 @@ def _updater(policy, O, **kw):
     return up
 
 
+def _autograd_grad(pol, buf, idx, kw, dtype):
+    """flat gradient of SB3's minibatch loss by torch-CPU autograd in `dtype` (+ the loss statistics)."""
+    p = copy.deepcopy(pol).to(dtype)
+    batch = tuple(t.to(dtype) for t in _oracle_batch(buf, idx))
+    loss, st = sb3_oracle.ppo_loss(p, *batch, **kw)
+    p.zero_grad()
+    loss.backward()
+    return p.flat_grads().numpy(), st
+
+
+# the last two rows are the bench workload's minibatch (bench.py: 18 944 samples = 148 tiles, KP = 16)
 @pytest.mark.parametrize("O,T,N,B,pre", [(14, 16, 40, 100, False), (14, 64, 37, 999, True),
-                                        (26, 32, 24, 500, False), (14, 8, 9, 1, False)])
+                                        (26, 32, 24, 500, False), (14, 8, 9, 1, False),
+                                        (14, 296, 64, 18944, False), (14, 296, 64, 18944, True)])
 def test_minibatch_gradient_matches_autograd(cuda_lib, golden_dir, O, T, N, B, pre):
     pol, buf = _make_problem(O, T, N, seed=O + T, pretrained_dir=golden_dir if pre else None)
     kw = dict(clip_range=0.2, ent_coef=0.05, vf_coef=0.5, normalize_advantage=True)
@@ -67,21 +79,26 @@ def test_minibatch_gradient_matches_autograd(cuda_lib, golden_dir, O, T, N, B, p
     n_mb = (N * T + B - 1) // B
     for mb in sorted({0, n_mb // 2, n_mb - 1}):  # includes the short last minibatch
         idx = perm[mb * B:(mb + 1) * B]
-        loss, st = sb3_oracle.ppo_loss(pol, *_oracle_batch(buf, idx), **kw)
-        pol.zero_grad()
-        loss.backward()
-        g_ref = pol.flat_grads().numpy()
+        g_ref, st = _autograd_grad(pol, buf, idx, kw, torch.float32)   # what SB3 computes
+        g_64, _ = _autograd_grad(pol, buf, idx, kw, torch.float64)     # what it approximates
         g = up.compute_grad(dbuf, dperm[mb * B:(mb + 1) * B], stats[mb], N, T).cpu().numpy()
         gp, tail = g[:up.n_params], g[up.stride - 16:]
-        err = np.abs(gp - g_ref).max() / np.abs(g_ref).max()
+        gmax = np.abs(g_ref).max()
+        err = np.abs(gp - g_ref).max() / gmax
         assert err < RTOL, f"minibatch {mb}: gradient error {err:.2e}"
-        # per-tensor check too (every tensor has its own scale)
+        # Per tensor (every tensor has its own scale): within 1e-5 of the float64 gradient, relative to the
+        # tensor's largest entry (floored at 1 % of the whole gradient's: a bias gradient is ONE sum over the
+        # minibatch that cancels to a small number, and torch's own float32 result is then no closer to the
+        # float64 value than ours -- the second assertion keeps us within 3x of torch's own rounding error).
         off = 0
         for name in sb3_oracle.PARAM_ORDER:
             n = dict(pol.named_parameters())[name].numel()
-            ref_t = g_ref[off:off + n]
-            e = np.abs(gp[off:off + n] - ref_t).max() / max(np.abs(ref_t).max(), 1e-3 * np.abs(g_ref).max())
-            assert e < 1e-4, f"{name}: {e:.2e}"
+            sl = slice(off, off + n)
+            scale = max(np.abs(g_64[sl]).max(), 1e-2 * gmax)
+            e = np.abs(gp[sl] - g_64[sl]).max() / scale
+            e_torch = np.abs(g_ref[sl] - g_64[sl]).max() / scale
+            assert e < 1e-5, f"{name}: {e:.2e} (torch float32 vs float64: {e_torch:.2e})"
+            assert e < max(3 * e_torch, 2e-6), f"{name}: {e:.2e} vs torch's own {e_torch:.2e}"
             off += n
         np.testing.assert_allclose(tail[0], st["policy_loss"], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(tail[1], st["value_loss"], rtol=1e-5)

@@ -180,24 +180,34 @@ def test_save_load_roundtrip_and_reference_zip(cuda_lib, golden_dir, tmp_path):
 
 
 def test_pretrained_point_policy_reaches_goals(cuda_lib, golden_dir):
-    """BASELINE configs[1] in small: deterministic shipped policy, goal reached within the 1000-step
-    limit; CUDA vs oracle on the same seeds (success rate within 1 %, as north_star asks)."""
+    """BASELINE configs[1] as written: the shipped point policy, deterministic, over 16 384 seeded
+    (init, goal) draws for 1000 steps -- examples/control.py:33-49 batched; success = goal reached within
+    the 1000-step limit of being set.  CUDA vs oracle on the same seeds: success rates within 1 %
+    (north_star), steps-to-goal within 1 %."""
     import sys
 
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import eval_policy
 
     z = os.path.join(golden_dir, "policies", "point-ppo.zip")
-    n = 96
-    g = eval_policy.evaluate_gpu(z, n, steps=400)
-    o = eval_policy.evaluate_oracle(z, n, steps=400)
-    assert abs(g["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.0105
-    assert o["first_goal_success_rate"] > 0.9
-    # un-saturated deterministic actions are sensitive (DESIGN.md "Sensitivity"): lengths may differ by a step or two
-    assert np.abs(g["first_len"] - o["first_len"]).max() <= 4
+    n = 16384
+    g = eval_policy.evaluate_gpu(z, n, steps=1000)
+    o = eval_policy.evaluate_oracle(z, n, steps=1000)
+    print(f"\nCONFIG2 point 16384 goals x 1000 steps: first-goal success gpu {g['first_goal_success_rate']:.5f} "
+          f"oracle {o['first_goal_success_rate']:.5f}; all goals gpu {g['all_goals_success_rate']:.5f} "
+          f"({g['goals_reached']} reached, {g['timeouts']} timeouts) oracle {o['all_goals_success_rate']:.5f} "
+          f"({o['goals_reached']} reached, {o['timeouts']} timeouts); mean steps to first goal gpu "
+          f"{g['first_goal_mean_steps']:.2f} oracle {o['first_goal_mean_steps']:.2f}; "
+          f"gpu {g['env_steps_per_s']:.3e} env-steps/s (unfused step + policy kernels)")
+    assert abs(g["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.01
+    assert abs(g["all_goals_success_rate"] - o["all_goals_success_rate"]) <= 0.01
+    assert o["first_goal_success_rate"] > 0.99
+    assert abs(g["first_goal_mean_steps"] / o["first_goal_mean_steps"] - 1.0) <= 0.01
+    assert abs(g["goals_reached"] / o["goals_reached"] - 1.0) <= 0.01
+    # un-saturated deterministic actions are sensitive (DESIGN.md "Sensitivity"): single episodes may differ by a
+    # few steps, the distribution does not
+    assert (np.abs(g["first_len"] - o["first_len"]) <= 4).mean() > 0.99
     assert (g["first_len"] == o["first_len"]).mean() > 0.6
-    big = eval_policy.evaluate_gpu(z, 4096, steps=400)
-    assert abs(big["first_goal_success_rate"] - o["first_goal_success_rate"]) <= 0.03
 
 
 def test_unfused_rollout_equals_fused(cuda_lib, golden_dir):

@@ -67,6 +67,7 @@ def evaluate_oracle(zip_path, n, horizon=1000, seed=0, steps=None):
     first_len = np.zeros(n, np.int64)
     first_ok = np.zeros(n, bool)
     seen = np.zeros(n, bool)
+    n_term = n_trunc = 0
     for _ in range(steps or horizon):
         with torch.no_grad():
             a = pol.predict_deterministic(torch.as_tensor(obs)).numpy()
@@ -75,9 +76,13 @@ def evaluate_oracle(zip_path, n, horizon=1000, seed=0, steps=None):
         first_len[new] = info["ep_l"][new]
         first_ok[new] = ~info["truncated"][new]
         seen |= done
+        n_term += int((done & ~info["truncated"]).sum())
+        n_trunc += int(info["truncated"].sum())
     ok = first_ok & seen
     return {"n_envs": n, "first_goal_success_rate": float(ok.mean()),
-            "first_goal_mean_steps": float(first_len[ok].mean()), "first_len": first_len, "first_ok": ok}
+            "first_goal_mean_steps": float(first_len[ok].mean()),
+            "all_goals_success_rate": n_term / max(n_term + n_trunc, 1), "goals_reached": n_term, "timeouts": n_trunc,
+            "first_len": first_len, "first_ok": ok}
 
 
 if __name__ == "__main__":
