@@ -4,11 +4,13 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA hot path)
   python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port of the
                                                              # reference stack on the host cores
+  python bench.py --env car --envs-per-gpu 16384            # BASELINE configs[3]
+  python bench.py --gpus 8 --envs-per-gpu 8192 [--env car]  # BASELINE configs[4] (under torchrun)
 
-A "step" is one PPO iteration of the workload in data/configs/point-ppo-b200.yaml on every
-rank: fused rollout of 296 steps x 4096 envs (1 212 416 env-steps), GAE, then 10 epochs x 64
-minibatches of 18 944 samples (forward, clipped loss, backward, grad-norm clip, Adam).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions used.
+A "step" is one PPO iteration of the workload (default: data/configs/point-ppo-b200.yaml) on every
+rank: rollout of n_steps x envs-per-gpu env-steps (point: ONE fused kernel), GAE, then 10 epochs of
+minibatches of 18 944 samples (forward, clipped loss, backward, grad-norm clip, Adam) in one persistent
+kernel per epoch.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
 from __future__ import annotations
 
@@ -24,17 +26,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ENVS = 4096          # per GPU (weak scaling)
+N_ENVS = 4096          # per GPU (weak scaling), default workload
 N_STEPS = 296
-BATCH = 18944
+BATCH = 18944          # = 148 SMs x 128-sample tiles
 N_EPOCHS = 10
-METRIC = "env-steps/sec (rollout+PPO update), point env"
-WORKLOAD = "point env 4096 parallel envs/GPU full rollout + GAE + PPO update (BASELINE.json configs[2])"
+DEFAULTS = {"point": (4096, 296), "car": (16384, 74)}   # (envs per GPU, n_steps): 64 minibatches per epoch each
+OBS_DIM = {"point": 14, "car": 26}
 
 # algorithmic work of the dominant kernel (ppo_epoch_tc_kernel), DESIGN.md "Kernels":
-# per sample and epoch: forward + backward-data + backward-weight of both 14-64-64 towers
-FLOP_PER_SAMPLE_EPOCH = 61056  # SURVEY.md section 8d, point
+# per sample and epoch: forward + backward-data + backward-weight of both O-64-64 towers
+FLOP_PER_SAMPLE_EPOCH = 61056
+FLOPS = {"point": 61056, "car": 70272}
 ENV_STEP_BYTES = 145           # SURVEY.md section 8d, stand-alone point env-step
+
+
+def metric_name(env):
+    return f"env-steps/sec (rollout+PPO update), {env} env"
+
+
+def workload_name(env, n_envs):
+    which = {("point", 4096): "configs[2]", ("car", 16384): "configs[3]", ("point", 8192): "configs[4] (8192/GPU)",
+             ("car", 8192): "configs[4] (8192/GPU, car)"}.get((env, n_envs), "custom size")
+    return f"{env} env {n_envs} parallel envs/GPU full rollout + GAE + PPO update (BASELINE.json {which})"
+
+
+METRIC = metric_name("point")
+WORKLOAD = workload_name("point", N_ENVS)
 
 
 def parse():
@@ -43,9 +60,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=148, help="rollout length of the CPU sample")
+    ap.add_argument("--env", default="point", choices=["point", "car"])
+    ap.add_argument("--envs-per-gpu", type=int, default=None, help="default 4096 (point) / 16384 (car)")
+    ap.add_argument("--n-steps", type=int, default=None, help="rollout length; default 296 (point) / 74 (car)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the stand-alone env-step roofline and the "
+                    "SB3-host-permutation e2e variant (they do not change value / e2e)")
+    a = ap.parse_args()
+    d_envs, d_steps = DEFAULTS[a.env]
+    a.envs_per_gpu = a.envs_per_gpu or d_envs
+    a.n_steps = a.n_steps or d_steps
+    return a
 
 
 # ------------------------------------------------------------------------------------------
@@ -111,7 +136,6 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------
 def cpu_port_step(n_envs, n_steps, batch, n_epochs, state):
     """One iteration of the reference algorithm on the host: oracle env + torch-CPU PPO."""
-    import numpy as np
     import torch
 
     from oracle import sb3_oracle
@@ -124,24 +148,44 @@ def cpu_port_step(n_envs, n_steps, batch, n_epochs, state):
     return n_envs * n_steps
 
 
-def cpu_port_setup(n_envs, n_steps, seed=0):
+def cpu_port_setup(n_envs, n_steps, seed=0, env="point"):
     import numpy as np
     import torch
 
-    from oracle import point_oracle as po, sb3_oracle
+    from oracle import sb3_oracle
     from oracle.vec_oracle import GoalVecOracle
 
+    if env == "point":
+        from oracle import point_oracle as po
+
+        body = po.PointBody(n_envs)
+    else:
+        from oracle import car_oracle as co
+
+        body = co.CarBody(n_envs)
     torch.manual_seed(seed)
-    pol = sb3_oracle.MlpPolicyOracle(14)
-    venv = GoalVecOracle(po.PointBody(n_envs), seed=seed, time_limit=1000, terminate_on_goal=True)
+    pol = sb3_oracle.MlpPolicyOracle(OBS_DIM[env])
+    venv = GoalVecOracle(body, seed=seed, time_limit=1000, terminate_on_goal=True)
     ro = sb3_oracle.RolloutOracle(venv, pol, n_steps, gamma=0.99, gae_lambda=0.5)
     return dict(ro=ro, pol=pol, opt=sb3_oracle.make_adam(pol), gen=torch.Generator().manual_seed(seed),
                 rng=np.random.RandomState(seed))
 
 
+def cpu_sample_shape(args):
+    """Workload of one CPU-arm step.  Point: the bench workload itself (same envs, rollout length,
+    minibatch size and epochs).  Car: the numpy car oracle (per-substep contact solves) runs at ~1.6e3
+    env-steps/s, so a step is a bounded sample of 1024 envs x 16 steps with proportionally small
+    minibatches (64 per epoch, as in the full workload)."""
+    if args.env == "point":
+        n_envs, T = args.envs_per_gpu, args.n_steps
+        return n_envs, T, min(BATCH, n_envs * T), True
+    n_envs, T = 1024, 16
+    return n_envs, T, n_envs * T // 64, False
+
+
 def run_reference(args):
-    """CPU arm: bounded sample of the same workload per step (same envs, same minibatch size and
-    epochs, shorter rollout) with every host thread torch / numpy will use."""
+    """CPU arm: the oracle port of the reference stack (numpy fp64 env + torch-CPU PPO = SB3's
+    arithmetic) with every host thread torch / numpy will use, on our arm's config."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -149,23 +193,27 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    T = args.cpu_sample_steps
-    batch = min(BATCH, N_ENVS * T)
-    state = cpu_port_setup(N_ENVS, T)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_port_step(N_ENVS, T, batch, N_EPOCHS, state)
+    n_envs, T, batch, same = cpu_sample_shape(args)
+    state = cpu_port_setup(n_envs, T, env=args.env)
+    for _ in range(args.warmup):
+        cpu_port_step(n_envs, T, batch, N_EPOCHS, state)
     t0 = time.perf_counter()
     done = 0
     for _ in range(args.steps):
-        done += cpu_port_step(N_ENVS, T, batch, N_EPOCHS, state)
+        done += cpu_port_step(n_envs, T, batch, N_EPOCHS, state)
     dt = time.perf_counter() - t0
     value = done / dt
-    sample = (f"{N_ENVS} envs x {T} steps per step ({N_ENVS * T} env-steps), {N_EPOCHS} epochs of "
-              f"minibatch {batch}; numpy fp64 oracle env + torch-CPU PPO (SB3 arithmetic)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+    sample = (f"{n_envs} envs x {T} steps per step ({n_envs * T} env-steps), {N_EPOCHS} epochs of "
+              f"minibatch {batch}; numpy fp64 oracle env + torch-CPU PPO (SB3 arithmetic)"
+              + ("; the full per-GPU workload of our arm" if same else "; bounded sample of our arm's workload"))
+    line = {"impl": "reference", "metric": metric_name(args.env), "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 physics / f32 PPO",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.env, args.envs_per_gpu), "n_envs_per_gpu": args.envs_per_gpu,
+                       "n_steps": args.n_steps, "batch_size": BATCH, "n_epochs": N_EPOCHS, "sample": sample,
+                       "same_workload_as_ours": same,
+                       "note": "one host runs ONE rank's share whatever --gpus says (the CPU arm does not shard)"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -196,13 +244,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    cfg = dict(env_name="point", time_limit=1000, n_envs=N_ENVS, vec_env_type="dummy", enable_gui=False, seed=0,
-               ppo_kwargs=dict(policy="MlpPolicy", n_steps=N_STEPS, n_epochs=N_EPOCHS, ent_coef=0.05,
-                               gae_lambda=0.5, batch_size=BATCH, verbose=0, host_permutation=False))
+    env_name, n_envs, n_steps = args.env, args.envs_per_gpu, args.n_steps
+    steps_per_iter = n_envs * n_steps  # per rank
+    if steps_per_iter % BATCH:
+        raise SystemExit(f"envs-per-gpu x n-steps = {steps_per_iter} is not a multiple of the minibatch {BATCH}")
+    # PPO's default index stream: mr_device_permutation (keyed Feistel bijection on the device);
+    # permutation="sb3" would reproduce numpy's stream bit for bit from the host (parity runs)
+    cfg = dict(env_name=env_name, time_limit=1000, n_envs=n_envs, vec_env_type="dummy", enable_gui=False, seed=0,
+               ppo_kwargs=dict(policy="MlpPolicy", n_steps=n_steps, n_epochs=N_EPOCHS, ent_coef=0.05,
+                               gae_lambda=0.5, batch_size=BATCH, verbose=0))
     ctrl = PPOCtrl.from_config(cfg)
     ctrl.ppo.tensorboard_log = None
     model = ctrl.ppo
-    steps_per_iter = N_ENVS * N_STEPS  # per rank
+    assert model.permutation == "device"
 
     def iteration():
         model.collect_rollouts()
@@ -246,68 +300,120 @@ def run_ours(args):
     peaks, peaks_src = measured_peaks()
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     tensor_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone
-    achieved = FLOP_PER_SAMPLE_EPOCH * steps_per_iter / (epoch_ms * 1e-3) / 1e12
-    roofline = {"kernel": "ppo_epoch_tc_kernel<16> (one launch = one epoch = 64 minibatch updates: tcgen05 forward/"
-                          "backward GEMMs, gradient reduction, clip, Adam)",
+    flops = FLOPS[env_name]
+    achieved = flops * steps_per_iter / (epoch_ms * 1e-3) / 1e12
+    default_cfg = (env_name, n_envs, n_steps) == ("point", N_ENVS, N_STEPS)
+    kp = 16 if OBS_DIM[env_name] + 1 <= 16 else 32
+    roofline = {"kernel": f"ppo_epoch_tc_kernel<{kp}> (one launch = one epoch = {steps_per_iter // BATCH} minibatch updates: "
+                          "tcgen05 forward/backward GEMMs, bulk-reduced gradient, clip, Adam)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES, "ms_per_launch": epoch_ms,
-                "algorithmic": f"{FLOP_PER_SAMPLE_EPOCH} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples per launch",
+                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES if default_cfg else None,
+                "ms_per_launch": epoch_ms,
+                "algorithmic": f"{flops} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples per launch",
                 "peak_source": f"bf16_tflops of MEASURED_PEAKS.json ({peaks_src})",
                 "tensor_flops_issued_per_algorithmic_flop": 3,
                 "frac_issued": 3 * achieved / tensor_peak,
                 "frac_of_fp32_fma_peak": achieved / fp32_peak,
                 "note": "fp32 products are formed from two fp16 parts per operand (3 MMAs per product, gradients within "
                         "1e-6 of torch fp32), so 3x the algorithmic FLOPs go through the tensor pipe; the kernel is bound by the "
-                        "per-minibatch dependency chain (3 grid barriers + L2 hand-offs), see profiles/",
+                        "per-minibatch dependency chain (element-wise passes between the GEMMs, one grid barrier), see profiles/",
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/ (per launch)",
                 "step_share": {"rollout_ms": rollout_ms, "update_ms": train_ms,
                                "epoch_kernel_ms_x_epochs": epoch_ms * N_EPOCHS}}
-    env_roof = time_env_step_kernel(dev, peaks)
+    env_roof = None
+    if default_cfg and not args.no_extras:
+        env_roof = time_env_step_kernel(dev, peaks)
 
-    # ---- e2e: the public API (PPOCtrl.learn) with SB3's host-side permutations (pinned H2D) and
-    #      per-iteration D2H of the training statistics / episode buffer ---------------------------------
-    model.permutation = "pool"   # host-drawn permutations (permfeed.py), pinned -> device every epoch
+    # ---- e2e: the public API, PPOCtrl.learn(), as a user calls it: host loop, logger and episode-buffer
+    #      reads (D2H from the device into pinned memory) every iteration --------------------------------
+    def timed_learn():
+        barrier()
+        model.learn(total_timesteps=steps_per_iter * world * 3, reset_num_timesteps=True)  # warm (logger paths too)
+        barrier()
+        t0 = time.perf_counter()
+        model.learn(total_timesteps=steps_per_iter * world * args.steps, reset_num_timesteps=True)
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        return steps_per_iter * world * args.steps / float(wall.item())
+
     model.verbose = 0
-    barrier()
-    model.learn(total_timesteps=steps_per_iter * world * 3, reset_num_timesteps=True)  # warm (logger paths too)
-    barrier()
     sampler.active = True
-    t0 = time.perf_counter()
-    model.learn(total_timesteps=steps_per_iter * world * args.steps, reset_num_timesteps=True)
-    barrier()
-    wall = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-    e2e_value = steps_per_iter * world * args.steps / float(wall.item())
+    e2e_value = timed_learn()
+    sampler.active = False
+    d2h = EP_D2H_BYTES + 12 * 4
+    e2e_host = None
+    if not args.no_extras and env_name == "point":
+        # SB3's own semantics for RolloutBuffer.get: permutations drawn on the HOST (thread pool, one iteration
+        # ahead) and copied from pinned memory every epoch
+        model.permutation = "pool"
+        e2e_host = {"value": timed_learn(), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": N_EPOCHS * steps_per_iter * 8 * world, "d2h_bytes_per_step": d2h * world,
+                    "what": "PPOCtrl.learn() with permutation='pool': int64 minibatch permutations drawn on the host "
+                            "and copied H2D every epoch (SB3 draws them on the host too)"}
+        model.permutation = "device"
     clocks = sampler.stop() if rank == 0 else None   # sampled every 20 ms inside the value and e2e timed regions
-    h2d = N_EPOCHS * steps_per_iter * 8  # int64 permutations, pinned -> device, per rank
-    d2h = EP_D2H_BYTES + 11 * 8
+
+    # ---- with several ranks: are they still the same model, and is the sharded update the single-GPU update? --
+    mg = None
+    if world > 1:
+        from mobrob_b200.selfcheck import sharded_update_check
+
+        torch.cuda.synchronize(dev)
+        digest = torch.stack([model.updater.params.double().sum(), model.updater.params.double().abs().sum(),
+                              model.updater.exp_avg_sq.double().sum()])
+        gathered = [torch.empty_like(model.updater.params) for _ in range(world)]
+        dist.all_gather(gathered, model.updater.params)
+        identical = all(torch.equal(gathered[0], g) for g in gathered)
+        chk = sharded_update_check(dev, modes=("fused",), obs_dim=OBS_DIM[env_name])
+        timed_out = bool(model._xchg.timed_out()) if model._xchg is not None else False
+        mg = {"identical": bool(identical and chk["fused"]["identical_across_ranks"]),
+              "params_identical_after_timed_region": bool(identical),
+              "param_digest_rank0": [float(x) for x in digest.tolist()],
+              "max_rel_vs_single": chk["fused"]["max_rel_vs_single"], "moved": chk["moved"],
+              "exchange_timed_out": bool(timed_out or chk["fused"]["exchange_timed_out"]),
+              "what": "all-gather of the parameters after the timed region (bit-identical on every rank); then the "
+                      "fused epoch kernel on a small sharded synthetic rollout against a single-GPU update of the whole "
+                      "rollout on rank 0 (mobrob_b200/selfcheck.py), difference relative to the update's size",
+              "ok": bool(identical and chk["ok"] and not timed_out)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        sys.exit(0 if mg is None or mg["ok"] else 3)
 
-    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 physics / f32 policy+PPO", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_envs_per_gpu": N_ENVS, "n_steps": N_STEPS, "batch_size": BATCH,
-                       "n_epochs": N_EPOCHS, "minibatches_per_epoch": steps_per_iter // BATCH,
+    line = {"metric": metric_name(env_name), "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 physics / f32 policy+PPO", "data": "synthetic",
+            "config": {"workload": workload_name(env_name, n_envs), "n_envs_per_gpu": n_envs, "n_steps": n_steps,
+                       "batch_size": BATCH, "n_epochs": N_EPOCHS, "minibatches_per_epoch": steps_per_iter // BATCH,
+                       "permutation": "device (mr_device_permutation, the PPO default)",
                        "parallelism": f"dp{world} (envs sharded, gradient all-reduce)",
-                       "l2": "no flush: every step rewrites its 102 MB rollout working set and reads 97 MB of "
-                             "fresh permutations (> 126 MB L2 together)"},
+                       "l2": f"no flush: every step rewrites its {steps_per_iter * 84 / 1e6:.0f} MB rollout working set and "
+                             f"gathers it in {N_EPOCHS} fresh random orders (126 MB L2)"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": d2h * world,
-                    "what": "PPOCtrl.learn(): minibatch permutations drawn on the host (thread pool, one "
-                            "iteration ahead) and copied from pinned memory every epoch; logger + episode-buffer "
-                            "reads (D2H) every iteration"},
-            "roofline": roofline, "roofline_env_step": env_roof}
+                    "what": "PPOCtrl.learn() wall clock (the call examples/train.py makes): host loop, callbacks, logger; "
+                            "every iteration reads the newest episodes and the update's statistics D2H into pinned memory. "
+                            "The workload has no per-step host inputs -- envs, action noise and minibatch indices live on "
+                            "the device (0 B H2D); e2e_sb3_host_stream is the variant whose indices come from the host"},
+            "roofline": roofline}
+    if e2e_host is not None:
+        line["e2e_sb3_host_stream"] = e2e_host
+    if env_roof is not None:
+        line["roofline_env_step"] = env_roof
+    if mg is not None:
+        line["multi_gpu_check"] = mg
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if mg is not None and not mg["ok"]:
+        sys.exit(3)
 
 
 EP_D2H_BYTES = 100 * 12 + 8
@@ -345,17 +451,14 @@ def time_epoch_kernel(model, dev):
 
 def time_env_step_kernel(dev, peaks):
     """Stand-alone env-step kernel at N = 2^22 envs (state >> L2): HBM roofline of K1."""
+    import numpy as np
     import torch
 
-    from mobrob_b200 import GpuVecEnv
+    from mobrob_b200 import GpuVecEnv, _lib as L, seeding
 
     n = 1 << 22
     env = GpuVecEnv("point", n, seed=None, time_limit=1000, terminate_on_goal=True, device=dev.index)
-    import numpy as np
-
     # cheap synthetic seeding for 4M envs: replicate a block of real PCG64 streams
-    from mobrob_b200 import seeding, _lib as L
-
     blk = 4096
     init, goal, eng = seeding.vec_env_streams(0, blk)
     reps = n // blk
@@ -386,19 +489,20 @@ def time_env_step_kernel(dev, peaks):
 
 
 def cpu_baseline(args):
+    """One step of the CPU arm's workload (see cpu_sample_shape)."""
     import torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    T = args.cpu_sample_steps
-    batch = min(BATCH, N_ENVS * T)
-    state = cpu_port_setup(N_ENVS, T)
+    n_envs, T, batch, same = cpu_sample_shape(args)
+    state = cpu_port_setup(n_envs, T, env=args.env)
     t0 = time.perf_counter()
-    done = cpu_port_step(N_ENVS, T, batch, N_EPOCHS, state)
+    done = cpu_port_step(n_envs, T, batch, N_EPOCHS, state)
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"one iteration of {N_ENVS} envs x {T} steps ({done} env-steps), {N_EPOCHS} epochs of "
-                      f"minibatch {batch}; numpy fp64 oracle env + torch-CPU PPO; {dt:.1f} s",
+            "sample": f"one iteration of {n_envs} envs x {T} steps ({done} env-steps), {N_EPOCHS} epochs of "
+                      f"minibatch {batch}; numpy fp64 oracle env + torch-CPU PPO; {dt:.1f} s"
+                      + ("; the full per-GPU workload" if same else "; bounded sample"),
             "reference_stack_historical": "1026 env-steps/s (SB3 + mujoco-py, 2 subproc envs; BASELINE.md)"}
 
 

@@ -308,29 +308,47 @@ __global__ void __launch_bounds__(256) perm_to_rows_kernel(const int64_t* __rest
     rows[i] = (int32_t)((int64_t)t * N + n);
 }
 
-// Device-side index stream for RolloutBuffer.get when the permutation need not come from the host:
-// out[i] = P(i), P a keyed bijection of [0, n) -- four rounds of (odd multiply, xor-shift, add key)
-// on the enclosing power-of-two domain, cycle-walked back into range.  One thread per index, no
-// sort (torch.randperm costs 0.17 ms per epoch at n = 1.2e6; this is a 10 MB store).
+// Device-side index stream for RolloutBuffer.get when the bit-for-bit numpy stream is not asked for:
+// out[i] = P(i), P a keyed bijection of [0, n) -- a 6-round Feistel network over the enclosing
+// power-of-two domain (split into two halves of bits / 2 and bits - bits / 2 bits, swapped every
+// round; round function = keyed 32-bit avalanche hash), cycle-walked back into range (at most 2 trips
+// on average).  Every index is one thread's private computation: no sort, no atomics, one 10 MB store
+// for an epoch of 1.2 M samples.  Round 1's four multiply-xorshift rounds were a narrow family with
+// weak low bits (modulo 2^k a product's low bits depend only on the operands' low bits); a Feistel
+// network with a strong round function has no such structure -- tests/test_device_perm_gpu.py holds it
+// to chi-square tests on positions x values, successive pairs and minibatch composition.
 struct PermKey {
-    uint32_t mul[4], add[4];
+    uint32_t key[6];
     int bits;
 };
-__device__ __forceinline__ uint32_t perm_mix(uint32_t x, const PermKey& K) {
-    const uint32_t mask = K.bits >= 32 ? 0xFFFFFFFFu : ((1u << K.bits) - 1u);
-    const int sh = (K.bits + 1) >> 1;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        x = (x * K.mul[r] + K.add[r]) & mask;
-        x ^= x >> sh;
-    }
+__device__ __forceinline__ uint32_t perm_round(uint32_t x, uint32_t k) {
+    x ^= k;
+    x *= 0x9E3779B1u;   // lowbias32-style avalanche: every output bit depends on every input bit
+    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    x *= 0xC2B2AE35u;
+    x ^= x >> 16;
     return x;
+}
+__device__ __forceinline__ uint32_t perm_feistel(uint32_t x, const PermKey& K) {
+    const int lb = K.bits >> 1, rb = K.bits - lb;          // left half: high lb bits, right half: low rb bits
+    uint32_t L = x >> rb, R = x & ((1u << rb) - 1u);
+    int wl = lb, wr = rb;                                   // widths travel with the halves
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const uint32_t f = perm_round(R, K.key[r]) & ((1u << wl) - 1u);
+        const uint32_t nl = R, nr = L ^ f;
+        L = nl; R = nr;
+        const int t = wl; wl = wr; wr = t;
+    }
+    return (L << wr) | R;   // six rounds: an even number of swaps, the halves are back at (lb, rb)
 }
 __global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ out, int64_t n, PermKey K) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t x = (uint32_t)i;
-    do { x = perm_mix(x, K); } while ((int64_t)x >= n);
+    do { x = perm_feistel(x, K); } while ((int64_t)x >= n);
     out[i] = (int64_t)x;
 }
 
@@ -675,17 +693,16 @@ int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t*
     MR_REQUIRE(out != nullptr, "NULL argument");
     MR_REQUIRE(n > 0 && n < (int64_t(1) << 31), "n out of range");
     PermKey K;
-    K.bits = 1;
+    K.bits = 2;   // both Feistel halves need at least one bit
     while ((int64_t(1) << K.bits) < n) ++K.bits;
     uint64_t x = seed ^ (stream_id * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull);
-    for (int r = 0; r < 4; ++r) {   // splitmix64 key schedule
+    for (int r = 0; r < 6; r += 2) {   // splitmix64 key schedule: two round keys per output
         uint64_t z = (x += 0x9E3779B97F4A7C15ull);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
-        K.mul[r] = (uint32_t)z | 1u;            // odd: invertible modulo 2^bits
-        K.mul[r] = (K.mul[r] & ~6u) | 4u;       // = 5 (mod 8): full-period style multiplier
-        K.add[r] = (uint32_t)(z >> 32);
+        K.key[r] = (uint32_t)z;
+        K.key[r + 1] = (uint32_t)(z >> 32);
     }
     device_perm_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, K);
     MR_CHECK_LAUNCH();

@@ -110,11 +110,12 @@ class PPO:
         self.normalize_advantage, self.ent_coef, self.vf_coef = normalize_advantage, ent_coef, vf_coef
         self.max_grad_norm, self.verbose, self.seed = max_grad_norm, verbose, seed
         self.tensorboard_log = tensorboard_log
-        # RolloutBuffer.get's index stream: "sb3" = np.random.permutation on the global MT19937
-        # (bit-for-bit SB3, serial on the host); "pool" = host threads drawing PCG64 streams keyed by
-        # (seed, iteration, epoch) one iteration ahead (permfeed.py); "device" = mr_device_permutation.
+        # RolloutBuffer.get's index stream.  "device" (default): mr_device_permutation, a keyed Feistel
+        # bijection computed where the samples live -- nothing crosses PCIe.  "sb3": np.random.permutation
+        # on the global MT19937, bit-for-bit SB3's stream, serial on the host (parity runs).  "pool": host
+        # threads drawing streams keyed by (seed, iteration, epoch) one iteration ahead (permfeed.py).
         if permutation is None:
-            permutation = "sb3" if host_permutation in (None, True) else "device"
+            permutation = "sb3" if host_permutation is True else "device"
         if permutation not in ("sb3", "pool", "device"):
             raise ValueError(f"Unknown permutation mode: {permutation}")
         self.permutation = permutation
