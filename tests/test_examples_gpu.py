@@ -56,7 +56,8 @@ def test_train_script_runs_unchanged(cuda_lib, tmp_path, golden_dir, env_name):
     ck = PPO.load(str(models / "timestep_1024_steps.zip"))
     assert ck.num_timesteps == 1024
     # SB3's log table (verbose: 1) with the reference run's keys
-    for key in ("rollout/", "ep_len_mean", "time/", "fps", "total_timesteps", "train/", "approx_kl", "clip_fraction",
+    # (rollout/ep_* only appear once an episode has ended: not guaranteed in 2048 steps of an untrained policy)
+    for key in ("time/", "fps", "total_timesteps", "train/", "approx_kl", "clip_fraction",
                 "entropy_loss", "explained_variance", "learning_rate", "policy_gradient_loss", "value_loss", "n_updates"):
         assert key in out.stdout, key
     # tensorboard events under data/policies/tmp/{env}-ppo/tensorboard (src/mobrob/rl_control/ppo.py:53-57)

@@ -89,7 +89,7 @@ def test_logger_keys_and_values_match_sb3(cuda_lib, golden_dir, tmp_path, monkey
             "train/clip_fraction": np.mean([s["clip_fraction"] for s in st]),
             "train/loss": st[-1]["loss"],
             "train/explained_variance": 1.0 - np.var(y - p) / np.var(y),
-            "train/std": float(torch.exp(ref_pol.log_std).mean()),
+            "train/std": float(torch.exp(ref_pol.log_std.detach()).mean()),
             "train/n_updates": E * (it + 1), "train/clip_range": 0.2, "train/learning_rate": 3e-4})
     eps = _episodes_of(bufs, model._last_episode_starts.cpu().numpy())
     assert 3 <= len(eps) <= 100
@@ -142,13 +142,21 @@ def test_bench_configuration_learns(cuda_lib):
         ppo_mod.Logger.dump = orig
     lens = [c.get("rollout/ep_len_mean") for c in curve if "rollout/ep_len_mean" in c]
     rews = [c.get("rollout/ep_rew_mean") for c in curve if "rollout/ep_rew_mean" in c]
-    print(f"\nLEARNING point 4096 envs: ep_len_mean first {lens[0]:.1f} -> last {lens[-1]:.1f}; ep_rew_mean first "
-          f"{rews[0]:.2f} -> last {rews[-1]:.2f} after {LEARN_ITERS} iterations ({LEARN_ITERS * n_envs * n_steps:.3g} env-steps)")
-    assert lens[-1] < LEARN_LEN_BOUND and lens[-1] < 0.5 * max(lens[:5])
-    assert rews[-1] > rews[0] + 3.0
     ev = [c["train/explained_variance"] for c in curve if "train/explained_variance" in c]
+    std = [c["train/std"] for c in curve if "train/std" in c]
+    # Monitor's window (the 100 newest episodes) starts with the lucky few that end inside the first rollouts;
+    # once the 1000-step time-outs of the untrained policy arrive the mean climbs (~650 around iteration 9),
+    # then collapses as the policy learns to drive to the goal (~190 from iteration ~20 on; the reference's own
+    # run ends at 119 after 1e6 steps of 100-sample minibatches)
+    early, late = max(lens[3:16]), float(np.mean(lens[-5:]))
+    print(f"\nLEARNING point 4096 envs: ep_len_mean peak (iterations 4-16) {early:.1f} -> mean of the last five {late:.1f}; "
+          f"ep_rew_mean min early {min(rews[3:16]):.2f} -> last {rews[-1]:.2f}; explained variance {ev[-1]:.3f}; "
+          f"std {std[0]:.2f} -> {std[-1]:.2f} after {LEARN_ITERS} iterations ({LEARN_ITERS * n_envs * n_steps:.3g} env-steps)")
+    assert early > 400.0 and late < LEARN_LEN_BOUND and late < 0.5 * early
+    assert rews[-1] > 6.0 and min(rews[3:16]) < rews[-1] - 1.0
     assert ev[-1] > 0.5   # the value function explains the returns it is trained on
+    assert std[-1] > 5.0 * std[0]   # exploration noise grows towards the shipped policies' bang-bang regime (sigma 20-140)
 
 
 LEARN_ITERS = 40
-LEARN_LEN_BOUND = 400.0
+LEARN_LEN_BOUND = 300.0
