@@ -420,7 +420,7 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 
 # dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
-EPOCH_KERNEL_DRAM_BYTES = 149.8e6  # 145.5 MB read + 4.2 MB written (profiles/r01_ncu_full_final.txt)
+EPOCH_KERNEL_DRAM_BYTES = 143.1e6  # 138.6 MB read + 4.5 MB written (profiles/r02_ncu_full.txt)
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
@@ -434,14 +434,15 @@ def time_epoch_kernel(model, dev):
     saved = [t.clone() for t in (up.params, up.exp_avg, up.exp_avg_sq, up.step)]
     perm = torch.randperm(T * N, device=dev, dtype=torch.int64)
     stats = up.adv_stats(b["advantages"], perm, BATCH, N, T)
+    up.pack(b)
     for _ in range(2):
-        up.train_epoch_fused(b, perm, stats, BATCH, N, T)
+        up.train_epoch_fused(None, perm, stats, BATCH, N, T)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     e0.record()
     for _ in range(reps):
-        up.train_epoch_fused(b, perm, stats, BATCH, N, T)
+        up.train_epoch_fused(None, perm, stats, BATCH, N, T)
     e1.record()
     torch.cuda.synchronize(dev)
     for t, sv in zip((up.params, up.exp_avg, up.exp_avg_sq, up.step), saved):

@@ -222,9 +222,15 @@ int mr_xchg_connect(mr_xchg* x, const uint8_t* h_all_handles);
 void mr_xchg_destroy(mr_xchg* x);
 /* *timed_out <- 1 if an in-kernel exchange gave up waiting for a peer since creation (synchronous read) */
 int mr_xchg_status(mr_xchg* x, int* timed_out);
+/* The epoch kernel gathers its minibatches from PACKED sample records, one per buffer row (t * N + n):
+ * mr_ppo_record_floats(obs_dim) floats = [obs | ret | 0.. | 1 | a0 a1 old_logp adv | ret 0 0 0] (96 B for
+ * the point robot, 160 B for the car).  mr_ppo_pack_samples builds them once per rollout (after GAE) from
+ * the RolloutBuffer arrays; rec is caller-owned, n_rows * mr_ppo_record_floats floats. */
+int mr_ppo_record_floats(int obs_dim);
+int mr_ppo_pack_samples(int obs_dim, const float* obs, const float* act, const float* old_logp, const float* adv,
+                        const float* ret, int64_t n_rows, float* rec, void* stream);
 int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
-                       const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       const float* rec, const int64_t* perm, int32_t* rows, int64_t n_samples,
                        int64_t batch_size, const double* stats, int64_t N, int64_t T,
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,

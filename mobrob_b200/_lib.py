@@ -49,7 +49,9 @@ _SIGNATURES = {
     "mr_xchg_connect": (c_int, [_P, _P]),
     "mr_xchg_destroy": (None, [_P]),
     "mr_xchg_status": (c_int, [_P, POINTER(c_int)]),
-    "mr_ppo_epoch_fused": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P,
+    "mr_ppo_record_floats": (c_int, [c_int]),
+    "mr_ppo_pack_samples": (c_int, [c_int, _P, _P, _P, _P, _P, c_int64, _P, _P]),
+    "mr_ppo_epoch_fused": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, c_int64, c_int64, _P,
                                    c_int64, c_int64, c_float, c_float, c_float, c_int, c_float, c_float,
                                    c_float, c_float, c_float, _P, _P, _P, _P, _P]),
     "mr_rollout": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64,

@@ -32,7 +32,8 @@ struct GradArgs {
     const float* adv;       // [T][N]
     const float* ret;       // [T][N]
     const int64_t* perm;    // [mb_size] env-major sample ids (n * T + t)
-    const int32_t* rows;    // tensor-core kernels: the same samples as time-major buffer rows (t * N + n)
+    const int32_t* rows;    // the same samples as time-major buffer rows (t * N + n)
+    const float* rec;       // epoch kernel: packed sample records [T * N][KP + 8] (mr_ppo_pack_samples)
     int64_t mb_size;
     const double* mb_stats; // (sum adv, sum adv^2, count) of the GLOBAL minibatch
     int64_t N, T;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_grad_tc_kernel(GradArgs A,
     tc::stage<KP>(C, A.params, O);
     const tc::Sched S{A.mb_size, A.mb_size, 1, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1)};
     tc::Pipe<KP> Q;
-    tc::pipe_start<KP>(Q, A, S, O, threadIdx.x & 127, threadIdx.x >> 7, C.tower == 0);
+    tc::pipe_start<KP, false>(Q, A, S, O, threadIdx.x & 127, threadIdx.x >> 7, C.tower == 0);
     __syncthreads();
     const tc::MbConst MK = tc::mb_const(A.mb_stats, 0, A.normalize_adv);
     tc::minibatch<KP>(C, A, S, MK, 0, Q, O, A.partials + (size_t)blockIdx.x * grad_stride(O));
@@ -297,6 +298,32 @@ train_summary_kernel(const float* __restrict__ info, int n_rows, const float* __
     }
 }
 
+// One packed record per buffer row (tc::Rec): [obs | ret | 0.. | 1 | a0 a1 old_logp adv | ret 0 0 0].
+// One thread per (row, 16-byte quad of the record): coalesced 16-byte stores, gathers hit L1 / L2.
+__global__ void __launch_bounds__(256)
+pack_samples_kernel(const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ old_logp,
+                    const float* __restrict__ adv, const float* __restrict__ ret, int64_t n_rows, int O, int KP,
+                    float* __restrict__ rec) {
+    const int qpr = (KP + 8) >> 2;   // quads per record
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * qpr) return;
+    const int64_t r = i / qpr;
+    const int qd = (int)(i - r * qpr);
+    float v[4];
+    if (4 * qd < KP) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * qd + e;
+            v[e] = k < O ? obs[r * O + k] : (k == O ? ret[r] : (k == KP - 1 ? 1.f : 0.f));
+        }
+    } else if (4 * qd == KP) {
+        v[0] = act[2 * r]; v[1] = act[2 * r + 1]; v[2] = old_logp[r]; v[3] = adv[r];
+    } else {
+        v[0] = ret[r]; v[1] = v[2] = v[3] = 0.f;
+    }
+    reinterpret_cast<float4*>(rec)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // env-major sample ids (RolloutBuffer.swap_and_flatten order, n * T + t) -> rows of the time-major
 // buffers (t * N + n), once per epoch, so that the gather in the tensor-core kernels needs no division
 __global__ void __launch_bounds__(256) perm_to_rows_kernel(const int64_t* __restrict__ perm, int64_t n_samples,
@@ -464,7 +491,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
     GradArgs A = E.G;
     const tc::Sched S{E.n_samples, E.batch, n_mb, c >> 1, G >> 1};
     tc::Pipe<KP> Q;
-    tc::pipe_start<KP>(Q, A, S, O, tid & 127, tid >> 7, C.tower == 0);
+    tc::pipe_start<KP, true>(Q, A, S, O, tid & 127, tid >> 7, C.tower == 0);
 
     // the tower's parameters and Adam moments: flat global arrays -> shared memory, TL order
     for (int i = tid; i < TL.size; i += tc::THREADS) {
@@ -486,7 +513,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
         if (m >= 2 && slice_t)
             __stcg(reinterpret_cast<float4*>(E.acc + (size_t)((m + 1) % 3) * acc_floats) + my_quad, make_float4(0.f, 0.f, 0.f, 0.f));
         MR_TR(2);
-        const tc::TileAcc T = tc::tiles<KP>(C, A, S, MK, m, Q, O);
+        const tc::TileAcc T = tc::tiles<KP, true>(C, A, S, MK, m, Q, O);
         if (T.any) {
             // the lane- and row-owned sums first (they do not need the last tile's dW1 GEMM, which finishes
             // meanwhile), then dW2 from TMEM and its bulk reduction, then dW1 and the sums
@@ -718,7 +745,7 @@ int mr_ppo_grad_partials(const float* params, int obs_dim, const float* obs, con
                "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     MR_REQUIRE(mb_size > 0, "empty minibatch");
-    GradArgs A{params, obs, act, old_logp, adv, ret, perm, nullptr, mb_size, mb_stats, N, T,
+    GradArgs A{params, obs, act, old_logp, adv, ret, perm, nullptr, nullptr, mb_size, mb_stats, N, T,
                clip_range, ent_coef, vf_coef, normalize_adv, partials};
     static OncePerDevice once;
     if (once.first()) {
@@ -885,16 +912,30 @@ void mr_xchg_destroy(mr_xchg* x) {
     delete x;
 }
 
+int mr_ppo_record_floats(int obs_dim) { return (obs_dim + 1 <= 16 ? 16 : 32) + 8; }
+
+int mr_ppo_pack_samples(int obs_dim, const float* obs, const float* act, const float* old_logp, const float* adv,
+                        const float* ret, int64_t n_rows, float* rec, void* stream) {
+    MR_REQUIRE(obs && act && old_logp && adv && ret && rec, "NULL argument");
+    MR_REQUIRE(obs_dim > 0 && obs_dim < 31, "obs_dim out of range (the record keeps ret at column obs_dim and 1 at KP - 1)");
+    MR_REQUIRE(n_rows > 0, "empty buffer");
+    const int kp = obs_dim + 1 <= 16 ? 16 : 32;
+    const int64_t quads = n_rows * ((kp + 8) >> 2);
+    pack_samples_kernel<<<ceil_div(quads, 256), 256, 0, (cudaStream_t)stream>>>(obs, act, old_logp, adv, ret, n_rows,
+                                                                                obs_dim, kp, rec);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
 int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t* step, int obs_dim,
-                       const float* obs, const float* act, const float* old_logp, const float* adv,
-                       const float* ret, const int64_t* perm, int32_t* rows, int64_t n_samples,
+                       const float* rec, const int64_t* perm, int32_t* rows, int64_t n_samples,
                        int64_t batch_size, const double* stats, int64_t N, int64_t T,
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream) {
-    MR_REQUIRE(params && exp_avg && exp_avg_sq && step && obs && act && old_logp && adv && ret && perm &&
-                   rows && stats && partials && grad, "NULL argument");
-    MR_REQUIRE(obs_dim > 0 && obs_dim < 32, "obs_dim out of range (the tensor-core kernels need obs_dim < 32)");
+    MR_REQUIRE(params && exp_avg && exp_avg_sq && step && rec && perm && rows && stats && partials && grad,
+               "NULL argument");
+    MR_REQUIRE(obs_dim > 0 && obs_dim < 31, "obs_dim out of range (the packed records need obs_dim < 31)");
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     MR_REQUIRE(n_samples < (int64_t(1) << 31) && N * T < (int64_t(1) << 31), "samples are indexed with 32 bits");
     cudaStream_t s = (cudaStream_t)stream;
@@ -908,7 +949,7 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
     // Everything the launch synchronises through lives in the CALLER's scratch (`partials`), so two
     // updaters (different streams) never share a barrier word: [3 accumulators | global sum | barrier word]
     EpochArgs E;
-    E.G = GradArgs{params, obs, act, old_logp, adv, ret, perm, rows, 0, stats, N, T,
+    E.G = GradArgs{params, nullptr, nullptr, nullptr, nullptr, nullptr, perm, rows, rec, 0, stats, N, T,
                    clip_range, ent_coef, vf_coef, normalize_adv, partials};
     E.n_samples = n_samples; E.batch = batch_size; E.stats = stats;
     E.params = params; E.exp_avg = exp_avg; E.exp_avg_sq = exp_avg_sq; E.step = step;

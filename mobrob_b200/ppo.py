@@ -346,6 +346,8 @@ class PPO:
             self._sum_scratch = torch.zeros(8, dtype=torch.float64, device=self.device)
         log = self._log
         k = 0
+        if self.update_mode == "fused":
+            up.pack(b)   # packed sample records, once per rollout: what the epoch kernel gathers from
         for epoch in range(self.n_epochs):
             perm = perms[epoch] if perms is not None else self._permutation(n, epoch)
             if not torch.is_tensor(perm):
@@ -360,7 +362,7 @@ class PPO:
                     from .updater import PeerExchange
 
                     self._xchg = PeerExchange(up.obs_dim, self.device)
-                up.train_epoch_fused(b, perm, stats, B, N, T, log[k:k + n_mb], self._xchg)
+                up.train_epoch_fused(None, perm, stats, B, N, T, log[k:k + n_mb], self._xchg)
                 k += n_mb
             elif d is None:                      # 3 launches per minibatch, looped in C
                 up.train_epoch(b, perm, stats, B, N, T, log[k:k + n_mb])

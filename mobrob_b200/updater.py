@@ -94,16 +94,28 @@ class PpoUpdater:
             self.lr, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, self.partials.data_ptr(),
             self.grad.data_ptr(), None if info is None else info.data_ptr(), self._stream()))
 
-    def train_epoch_fused(self, buf: dict, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int,
+    def pack(self, buf: dict) -> torch.Tensor:
+        """Packed sample records of a rollout (mr_ppo_pack_samples): what train_epoch_fused gathers from.
+        Build them once per rollout, after GAE; they stay valid for all epochs of the update."""
+        n_rows = buf["log_probs"].numel()
+        rf = int(self.lib.mr_ppo_record_floats(self.obs_dim))
+        if getattr(self, "_rec", None) is None or self._rec.numel() != n_rows * rf:
+            self._rec = torch.empty(n_rows * rf, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.mr_ppo_pack_samples(
+            self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
+            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), n_rows, self._rec.data_ptr(), self._stream()))
+        return self._rec
+
+    def train_epoch_fused(self, buf: dict | None, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int,
                           T: int, info: torch.Tensor | None = None, xchg=None):
         """One cooperative launch for the whole epoch; xchg (PeerExchange) adds the in-kernel
-        NVLink all-reduce of the gradient (stats must then be the all-reduced, global sums)."""
+        NVLink all-reduce of the gradient (stats must then be the all-reduced, global sums).
+        buf = the rollout arrays (packed here) or None to reuse the records of the last pack()."""
+        rec = self.pack(buf) if buf is not None else self._rec
         _lib.check(self.lib.mr_ppo_epoch_fused(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
-            self.obs_dim, buf["obs"].data_ptr(), buf["actions"].data_ptr(), buf["log_probs"].data_ptr(),
-            buf["advantages"].data_ptr(), buf["returns"].data_ptr(), perm.data_ptr(),
-            self.rows(perm.numel()).data_ptr(), perm.numel(), batch_size,
-            stats.data_ptr(), N, T, self.clip_range,
+            self.obs_dim, rec.data_ptr(), perm.data_ptr(), self.rows(perm.numel()).data_ptr(), perm.numel(),
+            batch_size, stats.data_ptr(), N, T, self.clip_range,
             self.ent_coef, self.vf_coef, int(self.normalize_advantage), self.lr, self.betas[0], self.betas[1],
             self.eps, self.max_grad_norm, self.partials.data_ptr(), self.grad.data_ptr(),
             None if info is None else info.data_ptr(), None if xchg is None else xchg.handle, self._stream()))

@@ -15,7 +15,7 @@ n_epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 env_n = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cfg = dict(env_name="point", time_limit=1000, n_envs=bench.N_ENVS, vec_env_type="dummy", enable_gui=False, seed=0,
            ppo_kwargs=dict(policy="MlpPolicy", n_steps=bench.N_STEPS, n_epochs=n_epochs, ent_coef=0.05,
-                           gae_lambda=0.5, batch_size=bench.BATCH, verbose=0, host_permutation=False))
+                           gae_lambda=0.5, batch_size=bench.BATCH, verbose=0, permutation="device"))
 ctrl = PPOCtrl.from_config(cfg)
 model = ctrl.ppo
 for _ in range(3):
