@@ -13,8 +13,16 @@
 //
 // Contacts: five candidate points (two rim points per wheel, one under the caster), three rows each
 // (normal, two tangents) with MuJoCo's soft-constraint reference acceleration and regulariser, solved
-// by matrix-free projected Gauss-Seidel on the plain mass matrix (columns M^-1 J^T are re-derived by
-// the structured solve, nothing is stored).  Approximation of MuJoCo's pyramidal Newton solver.
+// by projected Gauss-Seidel on the Delassus matrix A = J M^-1 J^T.  Approximation of MuJoCo's pyramidal
+// Newton solver.  A is formed ONCE per substep in closed form: with T_c the 3x3 map from a force at
+// contact c to the chassis torque-like right-hand side, the 3x3 block between contacts i and j is
+//     A_ij = I / m + T_i^T Jc^-1 T_j + (same wheel) p_i p_j^T / I_ax + (caster) C C^T / I_s
+// (rows / columns rotated to the world axes), 750 flops for all 15 unique blocks; the 120 unique
+// entries live in shared memory, one column per thread.  A sweep is then 15 row updates of 15
+// multiply-adds each.  (Round 1 re-derived a column M^-1 J^T by a structured solve inside every row
+// update -- 30 000 dependent fp64 operations per substep where this needs 5 000 with far more
+// instruction-level parallelism; the oracle still does, which makes the parity test a check of the
+// closed form as well.)
 #pragma once
 
 #include "common.cuh"
@@ -133,57 +141,65 @@ __device__ inline void solve(const Consts& K, const Loads& L, const Bias& B, Gen
 struct Contact {
     double rO[3], rB[3];  // contact point relative to the body origin / to the rotor centre (chassis frame)
     double dist, imp;
-    int body;             // 0 left wheel, 1 right wheel, 2 caster
     bool active;
 };
+// contact k: 0, 1 = the two rim points of the left wheel (body 0); 2, 3 = right wheel (body 1); 4 = caster (body 2)
+__host__ __device__ constexpr int body_of(int k) { return k < 4 ? (k >> 1) : 2; }
 
-// J_row * gen : acceleration (velocity) of the contact point along d (all chassis frame)
-__device__ inline double row_apply(const Contact& c, const double* d, const Gen& g) {
-    double t[3], acc[3];
-    cross3(g.wd, c.rO, t);
-    acc[0] = g.a[0] + t[0]; acc[1] = g.a[1] + t[1]; acc[2] = g.a[2] + t[2];
-    if (c.body < 2) {
-        const double sd = g.sd[c.body];  // sd * xhat x rB
-        acc[1] += -sd * c.rB[2];
-        acc[2] += sd * c.rB[1];
+// Geometry of candidate contact k at the current pose (zB = world z in the chassis frame, pz = body height).
+// Cheap (~40 flops), so it is recomputed where needed instead of kept alive across the sweeps.
+template <int k>
+__device__ __forceinline__ Contact contact_geometry(const Consts& K, const double* zB, double pz) {
+    Contact c;
+    double pt[3], ctr[3];
+    if (k < 4) {
+        double dn = sqrt(zB[1] * zB[1] + zB[2] * zB[2]);
+        dn = 1.0 / fmax(dn, 1e-12);
+        const double d[3] = {0.0, -zB[1] * dn, -zB[2] * dn};  // most downward direction normal to the axle
+        const double* pw = (k < 2) ? K.posWL : K.posWR;
+        const double end = (k & 1) ? HALF_LEN : -HALF_LEN;
+        ctr[0] = pw[0]; ctr[1] = pw[1]; ctr[2] = pw[2];
+        pt[0] = pw[0] + end + R_WHEEL * d[0]; pt[1] = pw[1] + R_WHEEL * d[1]; pt[2] = pw[2] + R_WHEEL * d[2];
     } else {
-        cross3(g.ud, c.rB, t);
-        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
+        ctr[0] = K.posC[0]; ctr[1] = K.posC[1]; ctr[2] = K.posC[2];
+        pt[0] = ctr[0] - R_CASTER * zB[0]; pt[1] = ctr[1] - R_CASTER * zB[1]; pt[2] = ctr[2] - R_CASTER * zB[2];
     }
-    return dot3(acc, d);
+    c.dist = pz + dot3(zB, pt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        pt[i] -= 0.5 * c.dist * zB[i];  // MuJoCo places the contact midway between the surfaces
+        c.rO[i] = pt[i];
+        c.rB[i] = pt[i] - ctr[i];
+    }
+    c.active = c.dist < 0.0;
+    const double x = fmin(fabs(c.dist) / IMP_WIDTH, 1.0);
+    c.imp = IMP_D0 + (IMP_DMAX - IMP_D0) * (x < 0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x));
+    return c;
 }
 
-__device__ inline void unit_load(const Contact& c, const double* d, Loads& L) {
-    L.f[0] = d[0]; L.f[1] = d[1]; L.f[2] = d[2];
-    cross3(c.rO, d, L.tO);
-    double tb[3];
-    cross3(c.rB, d, tb);
-    L.tL = c.body == 0 ? tb[0] : 0.0;
-    L.tR = c.body == 1 ? tb[0] : 0.0;
-    L.tc[0] = c.body == 2 ? tb[0] : 0.0;
-    L.tc[1] = c.body == 2 ? tb[1] : 0.0;
-    L.tc[2] = c.body == 2 ? tb[2] : 0.0;
-}
-
-// Everything one substep / one mj_forward needs at the current state.
+// Everything one substep / one mj_forward needs at the current state, except the contacts.
 struct Frame {
-    double R[9], Rb[9];
+    double R[9];
     Bias B;
     Loads smooth;     // gravity + motors + joint damping
-    Gen vel;          // chassis-frame generalised velocity
-    Contact c[5];
-    bool any_contact;
 };
 
-__device__ inline void make_frame(const Consts& K, const State& s, double c0, double c1, bool contacts, Frame& F) {
+// chassis-frame generalised velocity (the Jacobian maps it like an acceleration)
+__device__ inline void gen_velocity(const State& s, const double* R, Gen& vel) {
+    double Rb[9], ub[3];
+    quat2mat(s.qb, Rb);
+    mat3v(Rb, s.wb, ub);
+    mat3tv(R, s.v, vel.a);
+    vel.wd[0] = s.w[0]; vel.wd[1] = s.w[1]; vel.wd[2] = s.w[2];
+    vel.sd[0] = s.s[0]; vel.sd[1] = s.s[1];
+    vel.ud[0] = ub[0]; vel.ud[1] = ub[1]; vel.ud[2] = ub[2];
+}
+
+__device__ inline void make_frame(const Consts& K, const State& s, double c0, double c1, Frame& F) {
     quat2mat(s.q, F.R);
-    quat2mat(s.qb, F.Rb);
-    double ub[3];
-    mat3v(F.Rb, s.wb, ub);
-    mat3tv(F.R, s.v, F.vel.a);
-    F.vel.wd[0] = s.w[0]; F.vel.wd[1] = s.w[1]; F.vel.wd[2] = s.w[2];
-    F.vel.sd[0] = s.s[0]; F.vel.sd[1] = s.s[1];
-    F.vel.ud[0] = ub[0]; F.vel.ud[1] = ub[1]; F.vel.ud[2] = ub[2];
+    double Rb[9], ub[3];
+    quat2mat(s.qb, Rb);
+    mat3v(Rb, s.wb, ub);
     // bias
     double t[3], Hh[3];
     cross3(s.w, K.com, t);
@@ -206,129 +222,240 @@ __device__ inline void make_frame(const Consts& K, const State& s, double c0, do
     const double fg = -K.mass * GRAV;
     F.smooth.f[0] = fg * zB[0]; F.smooth.f[1] = fg * zB[1]; F.smooth.f[2] = fg * zB[2];
     cross3(K.com, F.smooth.f, F.smooth.tO);
-    // contacts
-    F.any_contact = false;
-    if (!contacts) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) F.c[k].active = false;
-        return;
+}
+
+// Per-thread scratch in shared memory: entry e of this thread at base + e * stride doubles (stride = threads
+// per block, so that a warp's accesses to one entry are contiguous).  Reads are `volatile` shared loads ON
+// PURPOSE: the sweep loop's operands are loop-invariant, and with plain loads the compiler hoisted all 165 of
+// them out of the loop -- into 330 registers' worth of values, i.e. into local-memory spills that then came
+// back from L2 (the shared-memory carve-out leaves almost no L1) at ~6 stalled warps per issued instruction.
+struct Scratch {
+    uint32_t base;     // shared-window byte address of this thread's entry 0
+    uint32_t stride;   // bytes between consecutive entries
+    __device__ __forceinline__ double ld(int e) const {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)e * stride));
+        return v;
     }
-    double dn = sqrt(zB[1] * zB[1] + zB[2] * zB[2]);
-    dn = 1.0 / fmax(dn, 1e-12);
-    const double d[3] = {0.0, -zB[1] * dn, -zB[2] * dn};  // most downward direction normal to the axle
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        Contact& c = F.c[k];
-        double pt[3], ctr[3];
-        if (k < 4) {
-            const double* pw = (k < 2) ? K.posWL : K.posWR;
-            const double end = (k & 1) ? HALF_LEN : -HALF_LEN;
-            ctr[0] = pw[0]; ctr[1] = pw[1]; ctr[2] = pw[2];
-            pt[0] = pw[0] + end + R_WHEEL * d[0]; pt[1] = pw[1] + R_WHEEL * d[1]; pt[2] = pw[2] + R_WHEEL * d[2];
-            c.body = k >> 1;
-        } else {
-            ctr[0] = K.posC[0]; ctr[1] = K.posC[1]; ctr[2] = K.posC[2];
-            pt[0] = ctr[0] - R_CASTER * zB[0]; pt[1] = ctr[1] - R_CASTER * zB[1]; pt[2] = ctr[2] - R_CASTER * zB[2];
-            c.body = 2;
-        }
-        c.dist = s.p[2] + dot3(zB, pt);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            pt[i] -= 0.5 * c.dist * zB[i];  // MuJoCo places the contact midway between the surfaces
-            c.rO[i] = pt[i];
-            c.rB[i] = pt[i] - ctr[i];
-        }
-        c.active = c.dist < 0.0;
-        const double x = fmin(fabs(c.dist) / IMP_WIDTH, 1.0);
-        c.imp = IMP_D0 + (IMP_DMAX - IMP_D0) * (x < 0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x));
-        F.any_contact |= c.active;
+    __device__ __forceinline__ void st(int e, double v) const {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + (uint32_t)e * stride), "d"(v) : "memory");
+    }
+};
+constexpr int N_ROWS = 15;                              // 5 contacts x (world x, world y, normal)
+constexpr int A_ENTRIES = N_ROWS * (N_ROWS + 1) / 2;    // packed upper triangle
+constexpr int SCR_RES = A_ENTRIES;                      // resid0[15]
+constexpr int SCR_REG = SCR_RES + N_ROWS;               // Rreg[15]
+constexpr int SCR_INV = SCR_REG + N_ROWS;               // 1 / (A_ii + Rreg_i)
+constexpr int SCR_TW = SCR_INV + N_ROWS;                // Tw[5][9]
+constexpr int SCR_PW = SCR_TW + 45;                     // p[5][3]
+constexpr int SCRATCH_DOUBLES = SCR_PW + 15;            // 225 doubles = 1800 B per thread
+__host__ __device__ constexpr int a_index(int i, int j) {   // i <= j
+    return i * N_ROWS - i * (i - 1) / 2 + (j - i);
+}
+__device__ __forceinline__ double a_get(const Scratch& S, int i, int j) { return i <= j ? S.ld(a_index(i, j)) : S.ld(a_index(j, i)); }
+
+// acceleration (velocity) of a contact point of `body` for chassis-frame generalised accelerations g, chassis frame
+__device__ __forceinline__ void point_acc(const Contact& c, int body, const Gen& g, double* acc) {
+    double t[3];
+    cross3(g.wd, c.rO, t);
+    acc[0] = g.a[0] + t[0]; acc[1] = g.a[1] + t[1]; acc[2] = g.a[2] + t[2];
+    if (body < 2) {
+        const double sd = g.sd[body];  // sd * xhat x rB
+        acc[1] += -sd * c.rB[2];
+        acc[2] += sd * c.rB[1];
+    } else {
+        cross3(g.ud, c.rB, t);
+        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
     }
 }
 
-// Projected Gauss-Seidel on the plain mass matrix; f[c][k]: k = 0,1 world-x / world-y tangents, 2 normal.
-__device__ inline void solve_contacts(const Consts& K, const Frame& F, double f[5][3]) {
+// Contact j's part of the set-up: its blocks (i <= j, j) of A, its right-hand sides and regularisers.
+template <int cj>
+__device__ __forceinline__ void contact_setup(const Consts& K, const State& s, const Frame& F, const Gen& vel, const Gen& a_free,
+                                              const Scratch& S) {
+    const double zB[3] = {F.R[6], F.R[7], F.R[8]};
+    const Contact ct = contact_geometry<cj>(K, zB, s.p[2]);
+    constexpr int body = body_of(cj);
+    const double im = 1.0 / K.mass, iax = 1.0 / K.I_ax, is = 1.0 / K.I_s;
+    const double rc[3] = {ct.rO[0] - K.com[0], ct.rO[1] - K.com[1], ct.rO[2] - K.com[2]};
+    // T = [rc]x - (caster) [rB]x - (wheel) xhat xhat^T [rB]x ; e = rotor centre - com
+    const double ex = rc[0] - ct.rB[0], ey = rc[1] - ct.rB[1], ez = rc[2] - ct.rB[2];
+    double T[9];
+    T[0] = 0.0; T[1] = -ez; T[2] = ey;
+    if (cj < 4) {
+        T[3] = rc[2];  T[4] = 0.0;    T[5] = -rc[0];
+        T[6] = -rc[1]; T[7] = rc[0];  T[8] = 0.0;
+    } else {
+        T[3] = ez;  T[4] = 0.0; T[5] = -ex;
+        T[6] = -ey; T[7] = ex;  T[8] = 0.0;
+    }
+    // Tw = T R^T (columns = T applied to the world axes), Vw = Jc^-1 Tw, p = R (xhat x rB)
+    double Twj[9], Vwj[9], pj[3];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) f[c][0] = f[c][1] = f[c][2] = 0.0;
-    if (!F.any_contact) return;
-    Gen a_free;
-    solve<false, true>(K, F.smooth, F.B, a_free);
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            Twj[3 * m + l] = T[3 * m] * F.R[3 * l] + T[3 * m + 1] * F.R[3 * l + 1] + T[3 * m + 2] * F.R[3 * l + 2];
+            S.st(SCR_TW + 9 * cj + 3 * m + l, Twj[3 * m + l]);
+        }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+            Vwj[3 * m + l] = K.Jinv0[3 * m] * Twj[l] + K.Jinv0[3 * m + 1] * Twj[3 + l] + K.Jinv0[3 * m + 2] * Twj[6 + l];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pj[k] = F.R[3 * k + 1] * (-ct.rB[2]) + F.R[3 * k + 2] * ct.rB[1];
+        S.st(SCR_PW + 3 * cj + k, pj[k]);
+    }
+#pragma unroll
+    for (int ci = 0; ci <= cj; ++ci) {
+        const bool same_wheel = cj < 4 && (ci >> 1) == (cj >> 1);   // contacts (0, 1) left wheel, (2, 3) right wheel
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                if (ci == cj && l < k) continue;   // symmetric diagonal block: upper part only
+                const double t0 = ci == cj ? Twj[k] : S.ld(SCR_TW + 9 * ci + k);
+                const double t1 = ci == cj ? Twj[3 + k] : S.ld(SCR_TW + 9 * ci + 3 + k);
+                const double t2 = ci == cj ? Twj[6 + k] : S.ld(SCR_TW + 9 * ci + 6 + k);
+                double v = t0 * Vwj[l] + t1 * Vwj[3 + l] + t2 * Vwj[6 + l];
+                if (k == l) v += im;
+                if (same_wheel) v += (ci == cj ? pj[k] : S.ld(SCR_PW + 3 * ci + k)) * pj[l] * iax;
+                S.st(a_index(3 * ci + k, 3 * cj + l), v);
+            }
+    }
+    if (cj == 4) {   // caster rotor term: C C^T / I_s with C = R [rB]x
+        double Cw[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double r0 = F.R[3 * k], r1 = F.R[3 * k + 1], r2 = F.R[3 * k + 2];
+            Cw[3 * k] = r1 * ct.rB[2] - r2 * ct.rB[1];
+            Cw[3 * k + 1] = -r0 * ct.rB[2] + r2 * ct.rB[0];
+            Cw[3 * k + 2] = r0 * ct.rB[1] - r1 * ct.rB[0];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = k; l < 3; ++l)
+                S.st(a_index(12 + k, 12 + l), S.ld(a_index(12 + k, 12 + l)) +
+                                                  (Cw[3 * k] * Cw[3 * l] + Cw[3 * k + 1] * Cw[3 * l + 1] + Cw[3 * k + 2] * Cw[3 * l + 2]) * is);
+    }
+    // right-hand sides and regularisers of the contact's three rows
     const double b_coef = 2.0 / (IMP_DMAX * TC);
     const double k_coef = 1.0 / (IMP_DMAX * IMP_DMAX * TC * TC * DR * DR);
-    double resid0[5][3];
-    const int order[3] = {2, 0, 1};
-    for (int c = 0; c < 5; ++c) {
-        for (int kk = 0; kk < 3; ++kk) {
-            const int k = order[kk];
-            const double d[3] = {F.R[3 * k], F.R[3 * k + 1], F.R[3 * k + 2]};  // world axis k, chassis frame
-            const double vrow = row_apply(F.c[c], d, F.vel);
-            const double aref = -b_coef * vrow - (k == 2 ? k_coef * F.c[c].imp * F.c[c].dist : 0.0);
-            resid0[c][k] = row_apply(F.c[c], d, a_free) - aref;
-        }
+    double av[3], aa[3];
+    point_acc(ct, body, vel, av);
+    point_acc(ct, body, a_free, aa);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double* d = &F.R[3 * k];   // world axis k, chassis frame
+        const double aref = -b_coef * dot3(av, d) - (k == 2 ? k_coef * ct.imp * ct.dist : 0.0);
+        const int i = 3 * cj + k;
+        const double Aii = S.ld(a_index(i, i));
+        const double Rreg = (1.0 - ct.imp) / ct.imp * Aii;
+        S.st(SCR_RES + i, dot3(aa, d) - aref);
+        S.st(SCR_REG + i, Rreg);
+        S.st(SCR_INV + i, 1.0 / (Aii + Rreg));
     }
-    Gen ac;
+}
+
+// Projected Gauss-Seidel on the Delassus matrix; fl[3 c + k]: k = 0, 1 world-x / world-y tangents, 2 normal.
+// Returns the mask of active contacts (0: fl is all zero).
+__device__ inline unsigned solve_contacts(const Consts& K, const State& s, const Frame& F, bool contacts, double (&fl)[N_ROWS],
+                                          const Scratch& S) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) ac.a[i] = ac.wd[i] = ac.ud[i] = 0.0;
-    ac.sd[0] = ac.sd[1] = 0.0;
-    Bias nob{};
+    for (int i = 0; i < N_ROWS; ++i) fl[i] = 0.0;
+    if (!contacts) return 0u;
+    unsigned active = 0u;
+    {
+        const double zB[3] = {F.R[6], F.R[7], F.R[8]};
+        active |= contact_geometry<0>(K, zB, s.p[2]).active ? 1u : 0u;
+        active |= contact_geometry<1>(K, zB, s.p[2]).active ? 2u : 0u;
+        active |= contact_geometry<2>(K, zB, s.p[2]).active ? 4u : 0u;
+        active |= contact_geometry<3>(K, zB, s.p[2]).active ? 8u : 0u;
+        active |= contact_geometry<4>(K, zB, s.p[2]).active ? 16u : 0u;
+    }
+    if (!active) return 0u;
+    {
+        Gen a_free, vel;
+        solve<false, true>(K, F.smooth, F.B, a_free);
+        gen_velocity(s, F.R, vel);
+        contact_setup<0>(K, s, F, vel, a_free, S);
+        contact_setup<1>(K, s, F, vel, a_free, S);
+        contact_setup<2>(K, s, F, vel, a_free, S);
+        contact_setup<3>(K, s, F, vel, a_free, S);
+        contact_setup<4>(K, s, F, vel, a_free, S);
+    }
+    // sweeps: rows in the order (normal, x, y) of every active contact
+#pragma unroll 1
     for (int sweep = 0; sweep < N_SWEEPS; ++sweep) {
-        for (int c = 0; c < 5; ++c) {
-            if (!F.c[c].active) continue;
-            for (int kk = 0; kk < 3; ++kk) {
-                const int k = order[kk];
-                const double d[3] = {F.R[3 * k], F.R[3 * k + 1], F.R[3 * k + 2]};
-                Loads ul;
-                unit_load(F.c[c], d, ul);
-                Gen col;
-                solve<false, false>(K, ul, nob, col);
-                const double Aii = row_apply(F.c[c], d, col);
-                const double Rreg = (1.0 - F.c[c].imp) / F.c[c].imp * Aii;
-                const double cur = f[c][k];
-                const double res = resid0[c][k] + row_apply(F.c[c], d, ac) + Rreg * cur;
-                double nw = cur - res / (Aii + Rreg);
-                if (k == 2) nw = fmax(nw, 0.0);
-                else { const double lim = MU * f[c][2]; nw = fmin(fmax(nw, -lim), lim); }
-                const double delta = nw - cur;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { ac.a[i] += delta * col.a[i]; ac.wd[i] += delta * col.wd[i]; ac.ud[i] += delta * col.ud[i]; }
-                ac.sd[0] += delta * col.sd[0]; ac.sd[1] += delta * col.sd[1];
-                f[c][k] = nw;
+        for (int c = 0; c < 5; ++c) {
+            if (!(active >> c & 1u)) continue;
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+                const int k = kk == 0 ? 2 : kk - 1;
+                const int i = 3 * c + k;
+                double r0 = S.ld(SCR_RES + i) + S.ld(SCR_REG + i) * fl[i], r1 = 0.0, r2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < N_ROWS; j += 3) {   // three independent chains
+                    r0 += a_get(S, i, j) * fl[j];
+                    r1 += a_get(S, i, j + 1) * fl[j + 1];
+                    r2 += a_get(S, i, j + 2) * fl[j + 2];
+                }
+                double nw = fl[i] - (r0 + (r1 + r2)) * S.ld(SCR_INV + i);
+                if (k == 2) nw = fmax(nw, 0.0);
+                else { const double lim = MU * fl[3 * c + 2]; nw = fmin(fmax(nw, -lim), lim); }
+                fl[i] = nw;
             }
         }
     }
+    return active;
 }
 
-__device__ inline void add_contact_loads(const Frame& F, const double f[5][3], Loads& L) {
+template <int c>
+__device__ __forceinline__ void add_contact_load(const Consts& K, const State& s, const Frame& F, const double (&fl)[N_ROWS], Loads& L) {
+    const double zB[3] = {F.R[6], F.R[7], F.R[8]};
+    const Contact ct = contact_geometry<c>(K, zB, s.p[2]);
+    constexpr int body = body_of(c);
+    // force in chassis frame: sum_k f_k * (world axis k in chassis frame)
+    double fb[3], t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fb[i] = fl[3 * c] * F.R[i] + fl[3 * c + 1] * F.R[3 + i] + fl[3 * c + 2] * F.R[6 + i];
+    L.f[0] += fb[0]; L.f[1] += fb[1]; L.f[2] += fb[2];
+    cross3(ct.rO, fb, t);
+    L.tO[0] += t[0]; L.tO[1] += t[1]; L.tO[2] += t[2];
+    cross3(ct.rB, fb, t);
+    if (body == 0) L.tL += t[0];
+    else if (body == 1) L.tR += t[0];
+    else { L.tc[0] += t[0]; L.tc[1] += t[1]; L.tc[2] += t[2]; }
+}
+
+__device__ inline void add_contact_loads(const Consts& K, const State& s, const Frame& F, unsigned active,
+                                         const double (&fl)[N_ROWS], Loads& L) {
     L = F.smooth;
-    if (!F.any_contact) return;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        if (!F.c[c].active) continue;
-        // force in chassis frame: sum_k f_k * (world axis k in chassis frame)
-        double fb[3], t[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) fb[i] = f[c][0] * F.R[i] + f[c][1] * F.R[3 + i] + f[c][2] * F.R[6 + i];
-        L.f[0] += fb[0]; L.f[1] += fb[1]; L.f[2] += fb[2];
-        cross3(F.c[c].rO, fb, t);
-        L.tO[0] += t[0]; L.tO[1] += t[1]; L.tO[2] += t[2];
-        cross3(F.c[c].rB, fb, t);
-        if (F.c[c].body == 0) L.tL += t[0];
-        else if (F.c[c].body == 1) L.tR += t[0];
-        else { L.tc[0] += t[0]; L.tc[1] += t[1]; L.tc[2] += t[2]; }
-    }
+    if (!active) return;
+    if (active & 1u) add_contact_load<0>(K, s, F, fl, L);
+    if (active & 2u) add_contact_load<1>(K, s, F, fl, L);
+    if (active & 4u) add_contact_load<2>(K, s, F, fl, L);
+    if (active & 8u) add_contact_load<3>(K, s, F, fl, L);
+    if (active & 16u) add_contact_load<4>(K, s, F, fl, L);
 }
 
-__device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts) {
+__device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts, const Scratch& S) {
     Frame F;
-    make_frame(K, s, c0, c1, contacts, F);
-    double f[5][3];
-    solve_contacts(K, F, f);
+    make_frame(K, s, c0, c1, F);
+    double fl[N_ROWS];
+    const unsigned active = solve_contacts(K, s, F, contacts, fl, S);
     Loads L;
-    add_contact_loads(F, f, L);
+    add_contact_loads(K, s, F, active, fl, L);
     Gen acc;
     solve<true, true>(K, L, F.B, acc);
-    double vdot[3], wbdot[3];
+    double vdot[3], wbdot[3], Rb[9];
+    quat2mat(s.qb, Rb);
     mat3v(F.R, acc.a, vdot);
-    mat3tv(F.Rb, acc.ud, wbdot);
+    mat3tv(Rb, acc.ud, wbdot);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s.v[i] += H * vdot[i]; s.w[i] += H * acc.wd[i]; s.wb[i] += H * wbdot[i]; }
     s.s[0] += H * acc.sd[0]; s.s[1] += H * acc.sd[1];
@@ -342,22 +469,25 @@ __device__ inline void substep(const Consts& K, State& s, double c0, double c1, 
 // Engine.obs(): sorted-key layout [accelerometer 0:3 | ballangvel_rear 3:6 | ballquat_rear (3x3) 6:15 |
 // goal_compass 15:17 | gyro 17:20 | magnetometer 20:23 | velocimeter 23:26]
 __device__ inline void sensors(const Consts& K, const State& s, double c0, double c1, float gx, float gy,
-                               bool contacts, float* o) {
+                               bool contacts, float* o, const Scratch& S) {
     Frame F;
-    make_frame(K, s, c0, c1, contacts, F);
-    double f[5][3];
-    solve_contacts(K, F, f);
+    make_frame(K, s, c0, c1, F);
+    double fl[N_ROWS];
+    const unsigned active = solve_contacts(K, s, F, contacts, fl, S);
     Loads L;
-    add_contact_loads(F, f, L);
+    add_contact_loads(K, s, F, active, fl, L);
     Gen acc;
     solve<false, true>(K, L, F.B, acc);
+    double Rb[9], vB[3];
+    quat2mat(s.qb, Rb);
+    mat3tv(F.R, s.v, vB);
     // accelerometer: R^T (vdot + g ez) = aB + g zB
     o[0] = (float)(acc.a[0] + GRAV * F.R[6]);
     o[1] = (float)(acc.a[1] + GRAV * F.R[7]);
     o[2] = (float)(acc.a[2] + GRAV * F.R[8]);
     o[3] = (float)s.wb[0]; o[4] = (float)s.wb[1]; o[5] = (float)s.wb[2];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[6 + i] = (float)F.Rb[i];
+    for (int i = 0; i < 9; ++i) o[6 + i] = (float)Rb[i];
     const double dv[3] = {(double)gx - s.p[0], (double)gy - s.p[1], GOAL_Z - s.p[2]};
     double e[3];
     mat3tv(F.R, dv, e);
@@ -365,7 +495,7 @@ __device__ inline void sensors(const Consts& K, const State& s, double c0, doubl
     o[15] = (float)(e[0] * inv); o[16] = (float)(e[1] * inv);
     o[17] = (float)s.w[0]; o[18] = (float)s.w[1]; o[19] = (float)s.w[2];
     o[20] = (float)(MAG_Y * F.R[3]); o[21] = (float)(MAG_Y * F.R[4]); o[22] = (float)(MAG_Y * F.R[5]);
-    o[23] = (float)F.vel.a[0]; o[24] = (float)F.vel.a[1]; o[25] = (float)F.vel.a[2];
+    o[23] = (float)vB[0]; o[24] = (float)vB[1]; o[25] = (float)vB[2];
 }
 
 }  // namespace car

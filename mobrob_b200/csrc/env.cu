@@ -181,20 +181,25 @@ __global__ void point_get_pos_kernel(PointState st, double* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------
-// car: same VecEnv kernels, one thread per env (state in local fp64, ~0.4 MFLOP per env-step)
+// car: same VecEnv kernels, one thread per env (state in fp64 registers; the contact solver's Delassus matrix
+// in shared memory, car::SCRATCH_DOUBLES per thread)
 constexpr int CAR_THREADS = 64;
+constexpr size_t CAR_SMEM = (size_t)car::SCRATCH_DOUBLES * sizeof(double) * CAR_THREADS;   // 112.5 KB: two CTAs per SM
+#define MR_CAR_SCRATCH() extern __shared__ __align__(16) double car_smem[]; \
+    const car::Scratch S{(uint32_t)__cvta_generic_to_shared(car_smem + threadIdx.x), (uint32_t)(CAR_THREADS * sizeof(double))}
 
 __global__ void __launch_bounds__(CAR_THREADS)
 car_step_kernel(CarSoA st, car::Consts K, EnvCfg cfg, const float2* __restrict__ act,
                 float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
                 uint8_t* __restrict__ trunc, float* __restrict__ term_obs, double* __restrict__ ep_ret,
                 int32_t* __restrict__ ep_len) {
+    MR_CAR_SCRATCH();
     const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
     if (i >= st.n) return;
     CarHot h = st.load(i);
     float2 a = act[i];
     float o[car::OBS], tobs[car::OBS];
-    StepResult r = car_env_step(K, h, st.cold, i, a.x, a.y, cfg, st.contacts != 0, o, tobs);
+    StepResult r = car_env_step(K, h, st.cold, i, a.x, a.y, cfg, st.contacts != 0, o, tobs, S);
     st.store(i, h);
     for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
     rew[i] = r.rew;
@@ -209,6 +214,7 @@ car_step_kernel(CarSoA st, car::Consts K, EnvCfg cfg, const float2* __restrict__
 
 __global__ void __launch_bounds__(CAR_THREADS)
 car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int first, float* __restrict__ obs) {
+    MR_CAR_SCRATCH();
     const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
     if (i >= st.n) return;
     if (mask && !mask[i]) return;
@@ -218,22 +224,34 @@ car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int
     st.store(i, h);
     if (obs) {
         float o[car::OBS];
-        car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o);
+        car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o, S);
         for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
     }
 }
 
 __global__ void __launch_bounds__(CAR_THREADS)
 car_obs_kernel(CarSoA st, car::Consts K, float* __restrict__ obs) {
+    MR_CAR_SCRATCH();
     const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
     if (i >= st.n) return;
     CarHot h = st.load(i);
     float o[car::OBS];
-    car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o);
+    car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o, S);
     for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
 }
 
 // reference view: qpos(13) = p quat thL thR qb ; qvel(11) = v w sL sR wb ; ctrl goal elapsed ep_ret
+// the car kernels' contact scratch exceeds the default 48 KB of dynamic shared memory: opt in once per device
+static int car_smem_optin() {
+    static OncePerDevice once;
+    if (once.first()) {
+        MR_CUDA(cudaFuncSetAttribute(car_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
+        MR_CUDA(cudaFuncSetAttribute(car_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
+        MR_CUDA(cudaFuncSetAttribute(car_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
+    }
+    return MR_OK;
+}
+
 __global__ void car_get_state_kernel(CarSoA st, double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.n) return;
@@ -428,8 +446,10 @@ int mr_env_reset(mr_env* env, const uint8_t* mask, int first, float* obs_out, vo
     cudaStream_t s = (cudaStream_t)stream;
     if (env->kind == MR_ENV_POINT)
         point_reset_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, mask, first, obs_out);
-    else
-        car_reset_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(env->car, env->carK, mask, first, obs_out);
+    else {
+        if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
+        car_reset_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, mask, first, obs_out);
+    }
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -452,10 +472,12 @@ int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* 
         kern<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(
             env->point, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs, ep_ret, ep_len,
             down ? -dist : dist);
-    } else
-        car_step_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(
+    } else {
+        if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
+        car_step_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(
             env->car, env->carK, env->cfg, reinterpret_cast<const float2*>(act), obs, rew, done, trunc, term_obs,
             ep_ret, ep_len);
+    }
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -465,8 +487,10 @@ int mr_env_get_obs(mr_env* env, float* obs_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (env->kind == MR_ENV_POINT)
         point_obs_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, obs_out);
-    else
-        car_obs_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, 0, s>>>(env->car, env->carK, obs_out);
+    else {
+        if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
+        car_obs_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, obs_out);
+    }
     MR_CHECK_LAUNCH();
     return MR_OK;
 }

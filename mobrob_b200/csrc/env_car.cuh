@@ -105,13 +105,13 @@ __device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool
 
 __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const EnvCold& cold, int64_t i,
                                           float a0, float a1, const EnvCfg& cfg, bool contacts, float* obs,
-                                          float* term_obs) {
+                                          float* term_obs, const car::Scratch& S) {
     StepResult r;
     h.cx = fminf(fmaxf(a0, -1.f), 1.f);
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
     const double prevx = h.s.p[0], prevy = h.s.p[1];
 #pragma unroll 1
-    for (int k = 0; k < car::FRAME_SKIP; ++k) car::substep(K, h.s, (double)h.cx, (double)h.cz, contacts);
+    for (int k = 0; k < car::FRAME_SKIP; ++k) car::substep(K, h.s, (double)h.cx, (double)h.cz, contacts, S);
     const double gx = (double)h.gx, gy = (double)h.gy;
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.s.p[0], h.s.p[1]);
@@ -127,11 +127,11 @@ __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
-    car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs);
+    car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs, S);
     if (r.done) {
         for (int k = 0; k < car::OBS; ++k) term_obs[k] = obs[k];
         car_reset(h, cold, i, !r.reach);
-        car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs);
+        car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs, S);
     }
     return r;
 }
