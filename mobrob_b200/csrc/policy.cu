@@ -10,7 +10,8 @@ constexpr int PF_E = 8;
 __global__ void __launch_bounds__(PF_WARPS * 32)
 policy_forward_kernel(const float* __restrict__ params, int O, const float* __restrict__ obs,
                       const float* __restrict__ eps, float* __restrict__ act,
-                      float* __restrict__ logp, float* __restrict__ val, int64_t n) {
+                      float* __restrict__ logp, float* __restrict__ val, int64_t n,
+                      const uint8_t* __restrict__ mask) {
     extern __shared__ __align__(16) float smem[];
     SmemW W = stage_weights(smem, params, O);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -23,6 +24,9 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
          tile += (int64_t)gridDim.x * PF_WARPS) {
         const int64_t s0 = tile * PF_E;
         const int rows = (int)min((int64_t)PF_E, n - s0);
+        // masked call (V(terminal_observation) of the rollout's time-out bootstrap): tiles without a flagged
+        // sample are skipped -- truncations are rare, so the launch costs next to nothing
+        if (mask && !__any_sync(0xffffffffu, lane < rows && mask[s0 + lane] != 0)) continue;
         // rows of the tile are contiguous in obs: coalesced read, transposed into obsT[k][e]
         for (int idx = lane; idx < PF_E * O; idx += 32) {
             int e = idx / O, k = idx - e * O;
@@ -50,9 +54,20 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
 
 using namespace mr;
 
+namespace mr {
+// mr_policy_forward restricted to the samples whose mask byte is set (others' outputs are left untouched)
+int policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
+                          float* logp, float* val, int64_t n, const uint8_t* mask, void* stream);
+}
+
 extern "C" int mr_policy_forward(const float* params, int obs_dim, const float* obs,
                                  const float* eps, float* act, float* logp, float* val,
                                  int64_t n, void* stream) {
+    return mr::policy_forward_masked(params, obs_dim, obs, eps, act, logp, val, n, nullptr, stream);
+}
+
+int mr::policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
+                              float* logp, float* val, int64_t n, const uint8_t* mask, void* stream) {
     MR_REQUIRE(params && obs && act, "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     if (n <= 0) return MR_OK;
@@ -65,7 +80,7 @@ extern "C" int mr_policy_forward(const float* params, int obs_dim, const float* 
     int64_t tiles = (n + PF_E - 1) / PF_E;
     int blocks = (int)std::min<int64_t>((tiles + PF_WARPS - 1) / PF_WARPS, (int64_t)sms * 2);
     policy_forward_kernel<<<blocks, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        params, obs_dim, obs, eps, act, logp, val, n);
+        params, obs_dim, obs, eps, act, logp, val, n, mask);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }

@@ -246,6 +246,9 @@ extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* la
 // contact solver is too heavy to share a warp with the MLP, and as a cross-check of the fused kernel.
 namespace mr {
 
+int policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
+                          float* logp, float* val, int64_t n, const uint8_t* mask, void* stream);   // policy.cu
+
 __global__ void noise_kernel(float* __restrict__ eps, int64_t N, uint64_t seed, uint64_t ctr, int64_t env_offset) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -323,7 +326,7 @@ extern "C" int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, f
         if (rc != MR_OK) return rc;
         rc = mr_env_step(env, act + t * N * 2, last_obs, rew_tmp, done, trunc, term_obs, ep_ret_n, ep_len_n, stream);
         if (rc != MR_OK) return rc;
-        rc = mr_policy_forward(params, O, term_obs, nullptr, act_tmp, nullptr, tv, N, stream);
+        rc = mr::policy_forward_masked(params, O, term_obs, nullptr, act_tmp, nullptr, tv, N, trunc, stream);
         if (rc != MR_OK) return rc;
         mr::record_kernel<<<nb, tb, 0, s>>>(N, rew_tmp, done, trunc, tv, (float)gamma, rew + t * N, last_starts,
                                            ep_ret_n, ep_len_n, ep_r, ep_l, ep_count, ring_cap);

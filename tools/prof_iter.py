@@ -1,5 +1,5 @@
 """One profiled PPO iteration (bench workload, n_epochs configurable) for ncu:
-  ncu --profile-from-start off ... python tools/prof_iter.py [n_epochs] [standalone_env_n]"""
+  ncu --profile-from-start off ... python tools/prof_iter.py [n_epochs] [standalone_env_n] [point|car]"""
 import os
 import sys
 
@@ -13,8 +13,10 @@ from mobrob_b200.rl_control.ppo import PPOCtrl
 
 n_epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 env_n = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-cfg = dict(env_name="point", time_limit=1000, n_envs=bench.N_ENVS, vec_env_type="dummy", enable_gui=False, seed=0,
-           ppo_kwargs=dict(policy="MlpPolicy", n_steps=bench.N_STEPS, n_epochs=n_epochs, ent_coef=0.05,
+env_name = sys.argv[3] if len(sys.argv) > 3 else "point"
+n_envs, n_steps = bench.DEFAULTS[env_name]
+cfg = dict(env_name=env_name, time_limit=1000, n_envs=n_envs, vec_env_type="dummy", enable_gui=False, seed=0,
+           ppo_kwargs=dict(policy="MlpPolicy", n_steps=n_steps, n_epochs=n_epochs, ent_coef=0.05,
                            gae_lambda=0.5, batch_size=bench.BATCH, verbose=0, permutation="device"))
 ctrl = PPOCtrl.from_config(cfg)
 model = ctrl.ppo
