@@ -212,7 +212,8 @@ int mr_ppo_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int64_t
  * memory: each CTA pushes its slice of the reduced gradient into every peer's inbox as tagged
  * packets and sums the ranks' slices in rank order (parameters stay bit-identical on all ranks).
  * A peer that stops delivering ends the wait after ~4 s and raises the flag mr_xchg_status reads.
- * rows [n_samples] int32 caller-owned scratch.  stats: the GLOBAL minibatches' sums (all-reduced by the
+ * rows [n_samples] int32 caller-owned scratch, filled from perm -- or, with perm = NULL, already holding the
+ * epoch's samples as buffer rows (mr_ppo_prepare_epochs).  stats: the GLOBAL minibatches' sums (all-reduced by the
  * host when several ranks train), which is all the kernel needs to know about the other ranks' shares. */
 typedef struct mr_xchg mr_xchg;
 /* Allocate this rank's inbox; h_handle_out receives its 64-byte CUDA IPC handle. */
@@ -248,6 +249,16 @@ int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_
  * (a pure function of (seed, stream_id); one thread per index, no sort).  For runs that keep
  * RolloutBuffer.get's indices on the device (PPO(permutation="device")). */
 int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* out, void* stream);
+/* `count` (1..32) permutations in one launch: out [count][n], h_stream_ids [count] in host memory. */
+int mr_device_permutations(uint64_t seed, const uint64_t* h_stream_ids, int count, int64_t n, int64_t* out,
+                           void* stream);
+
+/* What the epochs of one PPO.train need besides the parameters, for all epochs at once: per-minibatch
+ * advantage sums (as mr_ppo_adv_stats) and the samples as time-major buffer rows.  perm [n_epochs][n_samples]
+ * (one permutation per epoch), stats [n_epochs][n_mb][3] f64 out, rows [n_epochs][n_samples] int32 out.
+ * mr_ppo_epoch_fused then takes perm = NULL and rows = the epoch's row of `rows`. */
+int mr_ppo_prepare_epochs(const float* adv, const int64_t* perm, int n_epochs, int64_t n_samples, int64_t batch_size,
+                          int64_t N, int64_t T, double* stats, int32_t* rows, void* stream);
 
 /* Host-side minibatch index stream (no device work): out[0..n) <- a uniformly random permutation
  * of 0..n-1, a pure function of (seed, stream).  Replaces, for throughput runs, the

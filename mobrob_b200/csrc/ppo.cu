@@ -189,8 +189,11 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(AdamArgs A) {
 __global__ void __launch_bounds__(1024)
 adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ perm,
                  int64_t n_samples, int64_t batch, int64_t N, int64_t T,
-                 double* __restrict__ stats) {
-    const int64_t mb = blockIdx.x;
+                 double* __restrict__ stats, int n_mb) {
+    // several epochs in one launch: block b serves minibatch b % n_mb of permutation b / n_mb
+    perm += (int64_t)(blockIdx.x / n_mb) * n_samples;
+    stats += (int64_t)(blockIdx.x / n_mb) * n_mb * 3;
+    const int64_t mb = blockIdx.x % n_mb;
     const int64_t s0 = mb * batch, s1 = min(n_samples, s0 + batch);
     double s = 0.0, q = 0.0;
     constexpr int U = 4;   // independent gathers in flight per thread
@@ -371,12 +374,17 @@ __device__ __forceinline__ uint32_t perm_feistel(uint32_t x, const PermKey& K) {
     }
     return (L << wr) | R;   // six rounds: an even number of swaps, the halves are back at (lb, rb)
 }
-__global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ out, int64_t n, PermKey K) {
+constexpr int MAX_PERMS = 32;   // permutations per launch (one per epoch of an update)
+struct PermKeys {
+    PermKey k[MAX_PERMS];
+};
+__global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ out, int64_t n, PermKeys Ks) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const PermKey& K = Ks.k[blockIdx.y];   // blockIdx.y: which permutation
     uint32_t x = (uint32_t)i;
     do { x = perm_feistel(x, K); } while ((int64_t)x >= n);
-    out[i] = (int64_t)x;
+    out[(int64_t)blockIdx.y * n + i] = (int64_t)x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -711,14 +719,12 @@ int mr_ppo_adv_stats(const float* adv, const int64_t* perm, int64_t n_samples, i
     MR_REQUIRE(adv && perm && stats, "NULL argument");
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     int n_mb = ceil_div(n_samples, batch_size);
-    adv_stats_kernel<<<n_mb, 1024, 0, (cudaStream_t)stream>>>(adv, perm, n_samples, batch_size, N, T, stats);
+    adv_stats_kernel<<<n_mb, 1024, 0, (cudaStream_t)stream>>>(adv, perm, n_samples, batch_size, N, T, stats, n_mb);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
 
-int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* out, void* stream) {
-    MR_REQUIRE(out != nullptr, "NULL argument");
-    MR_REQUIRE(n > 0 && n < (int64_t(1) << 31), "n out of range");
+static PermKey make_perm_key(uint64_t seed, uint64_t stream_id, int64_t n) {
     PermKey K;
     K.bits = 2;   // both Feistel halves need at least one bit
     while ((int64_t(1) << K.bits) < n) ++K.bits;
@@ -731,7 +737,39 @@ int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t*
         K.key[r] = (uint32_t)z;
         K.key[r + 1] = (uint32_t)(z >> 32);
     }
-    device_perm_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, K);
+    return K;
+}
+
+int mr_device_permutations(uint64_t seed, const uint64_t* h_stream_ids, int count, int64_t n, int64_t* out, void* stream) {
+    MR_REQUIRE(out != nullptr && h_stream_ids != nullptr, "NULL argument");
+    MR_REQUIRE(n > 0 && n < (int64_t(1) << 31), "n out of range");
+    MR_REQUIRE(count > 0 && count <= MAX_PERMS, "1 to 32 permutations per call");
+    PermKeys Ks{};
+    for (int e = 0; e < count; ++e) Ks.k[e] = make_perm_key(seed, h_stream_ids[e], n);
+    device_perm_kernel<<<dim3(ceil_div(n, 256), count), 256, 0, (cudaStream_t)stream>>>(out, n, Ks);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+int mr_device_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* out, void* stream) {
+    return mr_device_permutations(seed, &stream_id, 1, n, out, stream);
+}
+
+// Everything the epochs of one update need besides the parameters, for ALL epochs in two launches: the
+// per-minibatch advantage sums (mr_ppo_adv_stats) and the samples as buffer rows.  perm [n_epochs][n_samples],
+// stats [n_epochs][n_mb][3], rows [n_epochs][n_samples].  The permutations do not depend on the update, so
+// nothing forces these small latency-bound kernels in between the epoch kernels (30 launches, 0.5 ms per
+// iteration of the bench workload; with several ranks also ten NCCL calls instead of one).
+int mr_ppo_prepare_epochs(const float* adv, const int64_t* perm, int n_epochs, int64_t n_samples, int64_t batch_size,
+                          int64_t N, int64_t T, double* stats, int32_t* rows, void* stream) {
+    MR_REQUIRE(adv && perm && stats && rows, "NULL argument");
+    MR_REQUIRE(batch_size > 0 && n_samples > 0 && n_epochs > 0, "empty batch");
+    MR_REQUIRE(n_samples * n_epochs < (int64_t(1) << 40) && N * T < (int64_t(1) << 31), "sizes out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_mb = ceil_div(n_samples, batch_size);
+    adv_stats_kernel<<<n_mb * n_epochs, 1024, 0, s>>>(adv, perm, n_samples, batch_size, N, T, stats, n_mb);
+    MR_CHECK_LAUNCH();
+    perm_to_rows_kernel<<<ceil_div(n_samples * n_epochs, 256), 256, 0, s>>>(perm, n_samples * n_epochs, N, T, rows);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
@@ -933,8 +971,8 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
                        float clip_range, float ent_coef, float vf_coef, int normalize_adv, float lr,
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream) {
-    MR_REQUIRE(params && exp_avg && exp_avg_sq && step && rec && perm && rows && stats && partials && grad,
-               "NULL argument");
+    MR_REQUIRE(params && exp_avg && exp_avg_sq && step && rec && rows && stats && partials && grad,
+               "NULL argument");   // perm may be NULL: rows then already hold the epoch's samples (mr_ppo_prepare_epochs)
     MR_REQUIRE(obs_dim > 0 && obs_dim < 31, "obs_dim out of range (the packed records need obs_dim < 31)");
     MR_REQUIRE(batch_size > 0 && n_samples > 0, "empty batch");
     MR_REQUIRE(n_samples < (int64_t(1) << 31) && N * T < (int64_t(1) << 31), "samples are indexed with 32 bits");
@@ -981,8 +1019,10 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
         MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         MR_CUDA(cudaFuncSetAttribute(ppo_epoch_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     }
-    perm_to_rows_kernel<<<ceil_div(n_samples, 256), 256, 0, s>>>(perm, n_samples, N, T, rows);
-    MR_CHECK_LAUNCH();
+    if (perm) {
+        perm_to_rows_kernel<<<ceil_div(n_samples, 256), 256, 0, s>>>(perm, n_samples, N, T, rows);
+        MR_CHECK_LAUNCH();
+    }
     int O = obs_dim;
     void* args[] = {&E, &O};
     const void* fn = kp == 16 ? (const void*)ppo_epoch_tc_kernel<16> : (const void*)ppo_epoch_tc_kernel<32>;

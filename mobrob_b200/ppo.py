@@ -327,6 +327,20 @@ class PPO:
         _lib.check(self.lib.mr_device_permutation(int(self.seed or 0), key, n, out.data_ptr(), self._stream()))
         return out
 
+    def _device_permutations(self, n):
+        """All epochs' index streams of this update in one launch: [n_epochs, n] int64 (mr_device_permutations)."""
+        import ctypes
+
+        E = self.n_epochs
+        if getattr(self, "_dperm_all", None) is None or self._dperm_all.shape != (E, n):
+            self._dperm_all = torch.empty((E, n), dtype=torch.int64, device=self.device)
+        d = _dist()
+        rank = d.get_rank() if d is not None else 0
+        keys = (ctypes.c_uint64 * E)(*[(rank << 48) ^ (self._train_count << 16) ^ e for e in range(E)])
+        _lib.check(self.lib.mr_device_permutations(int(self.seed or 0), keys, E, n, self._dperm_all.data_ptr(),
+                                                   self._stream()))
+        return self._dperm_all
+
     def train(self, perms=None):
         """PPO.train: n_epochs passes of minibatch updates.  perms: optional list of int64 index
         arrays (one per epoch) for parity runs; otherwise drawn like RolloutBuffer.get."""
@@ -348,7 +362,25 @@ class PPO:
         k = 0
         if self.update_mode == "fused":
             up.pack(b)   # packed sample records, once per rollout: what the epoch kernel gathers from
-        for epoch in range(self.n_epochs):
+            if d is not None and self._xchg is None:
+                from .updater import PeerExchange
+
+                self._xchg = PeerExchange(up.obs_dim, self.device)
+        if self.update_mode == "fused" and perms is None and self.permutation == "device" and self.n_epochs <= 32:
+            # the whole update's index streams, advantage sums and row indices up front (3 launches and, with
+            # several ranks, ONE all-reduce), then nothing but the epoch kernels back to back
+            perm_all = self._device_permutations(n)
+            stats_all, rows_all = up.prepare_epochs(b["advantages"], perm_all, B, N, T)
+            if d is not None:
+                flat, _ = sharding.allreduce_adv_stats(stats_all.view(-1, 3))
+                stats_all = flat.view(self.n_epochs, n_mb, 3)
+            for epoch in range(self.n_epochs):
+                up.train_epoch_fused(None, None, stats_all[epoch], B, N, T, log[k:k + n_mb], self._xchg, rows=rows_all[epoch])
+                k += n_mb
+            epochs = ()
+        else:
+            epochs = range(self.n_epochs)
+        for epoch in epochs:
             perm = perms[epoch] if perms is not None else self._permutation(n, epoch)
             if not torch.is_tensor(perm):
                 perm = torch.as_tensor(np.asarray(perm, dtype=np.int64))
@@ -358,10 +390,6 @@ class PPO:
             if d is not None:
                 stats, share = sharding.allreduce_adv_stats(stats)
             if self.update_mode == "fused":      # one cooperative launch per epoch (+ NVLink all-reduce)
-                if d is not None and self._xchg is None:
-                    from .updater import PeerExchange
-
-                    self._xchg = PeerExchange(up.obs_dim, self.device)
                 up.train_epoch_fused(None, perm, stats, B, N, T, log[k:k + n_mb], self._xchg)
                 k += n_mb
             elif d is None:                      # 3 launches per minibatch, looped in C

@@ -106,15 +106,29 @@ class PpoUpdater:
             buf["advantages"].data_ptr(), buf["returns"].data_ptr(), n_rows, self._rec.data_ptr(), self._stream()))
         return self._rec
 
-    def train_epoch_fused(self, buf: dict | None, perm: torch.Tensor, stats: torch.Tensor, batch_size: int, N: int,
-                          T: int, info: torch.Tensor | None = None, xchg=None):
+    def prepare_epochs(self, adv: torch.Tensor, perms: torch.Tensor, batch_size: int, N: int, T: int):
+        """All epochs of an update at once: perms [E, n] int64 -> (stats [E, n_mb, 3] float64, rows [E, n] int32)."""
+        E, n = perms.shape
+        n_mb = (n + batch_size - 1) // batch_size
+        stats = torch.empty((E, n_mb, 3), dtype=torch.float64, device=self.device)
+        if getattr(self, "_rows_all", None) is None or self._rows_all.shape != (E, n):
+            self._rows_all = torch.empty((E, n), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mr_ppo_prepare_epochs(adv.data_ptr(), perms.data_ptr(), E, n, batch_size, N, T,
+                                                  stats.data_ptr(), self._rows_all.data_ptr(), self._stream()))
+        return stats, self._rows_all
+
+    def train_epoch_fused(self, buf: dict | None, perm: torch.Tensor | None, stats: torch.Tensor, batch_size: int, N: int,
+                          T: int, info: torch.Tensor | None = None, xchg=None, rows: torch.Tensor | None = None):
         """One cooperative launch for the whole epoch; xchg (PeerExchange) adds the in-kernel
         NVLink all-reduce of the gradient (stats must then be the all-reduced, global sums).
-        buf = the rollout arrays (packed here) or None to reuse the records of the last pack()."""
+        buf = the rollout arrays (packed here) or None to reuse the records of the last pack().
+        Either perm (int64 env-major sample ids) or rows (one row of prepare_epochs' output) names the samples."""
         rec = self.pack(buf) if buf is not None else self._rec
+        n = perm.numel() if perm is not None else rows.numel()
         _lib.check(self.lib.mr_ppo_epoch_fused(
             self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr(),
-            self.obs_dim, rec.data_ptr(), perm.data_ptr(), self.rows(perm.numel()).data_ptr(), perm.numel(),
+            self.obs_dim, rec.data_ptr(), None if perm is None else perm.data_ptr(),
+            self.rows(n).data_ptr() if rows is None else rows.data_ptr(), n,
             batch_size, stats.data_ptr(), N, T, self.clip_range,
             self.ent_coef, self.vf_coef, int(self.normalize_advantage), self.lr, self.betas[0], self.betas[1],
             self.eps, self.max_grad_norm, self.partials.data_ptr(), self.grad.data_ptr(),
