@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--env", default="point", choices=["point", "car"])
     ap.add_argument("--envs-per-gpu", type=int, default=None, help="default 4096 (point) / 16384 (car)")
     ap.add_argument("--n-steps", type=int, default=None, help="rollout length; default 296 (point) / 74 (car)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="minibatch size per GPU (multiple of 128; default 18944)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the stand-alone env-step roofline and the "
                     "SB3-host-permutation e2e variant (they do not change value / e2e)")
@@ -178,7 +179,7 @@ def cpu_sample_shape(args):
     minibatches (64 per epoch, as in the full workload)."""
     if args.env == "point":
         n_envs, T = args.envs_per_gpu, args.n_steps
-        return n_envs, T, min(BATCH, n_envs * T), True
+        return n_envs, T, min(args.batch, n_envs * T), True
     n_envs, T = 1024, 16
     return n_envs, T, n_envs * T // 64, False
 
@@ -211,7 +212,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 physics / f32 PPO",
             "data": "synthetic",
             "config": {"workload": workload_name(args.env, args.envs_per_gpu), "n_envs_per_gpu": args.envs_per_gpu,
-                       "n_steps": args.n_steps, "batch_size": BATCH, "n_epochs": N_EPOCHS, "sample": sample,
+                       "n_steps": args.n_steps, "batch_size": args.batch, "n_epochs": N_EPOCHS, "sample": sample,
                        "same_workload_as_ours": same,
                        "note": "one host runs ONE rank's share whatever --gpus says (the CPU arm does not shard)"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -246,13 +247,14 @@ def run_ours(args):
 
     env_name, n_envs, n_steps = args.env, args.envs_per_gpu, args.n_steps
     steps_per_iter = n_envs * n_steps  # per rank
-    if steps_per_iter % BATCH:
-        raise SystemExit(f"envs-per-gpu x n-steps = {steps_per_iter} is not a multiple of the minibatch {BATCH}")
+    batch = args.batch
+    if steps_per_iter % batch:
+        raise SystemExit(f"envs-per-gpu x n-steps = {steps_per_iter} is not a multiple of the minibatch {batch}")
     # PPO's default index stream: mr_device_permutation (keyed Feistel bijection on the device);
     # permutation="sb3" would reproduce numpy's stream bit for bit from the host (parity runs)
     cfg = dict(env_name=env_name, time_limit=1000, n_envs=n_envs, vec_env_type="dummy", enable_gui=False, seed=0,
                ppo_kwargs=dict(policy="MlpPolicy", n_steps=n_steps, n_epochs=N_EPOCHS, ent_coef=0.05,
-                               gae_lambda=0.5, batch_size=BATCH, verbose=0))
+                               gae_lambda=0.5, batch_size=batch, verbose=0))
     ctrl = PPOCtrl.from_config(cfg)
     ctrl.ppo.tensorboard_log = None
     model = ctrl.ppo
@@ -296,15 +298,15 @@ def run_ours(args):
     ev[2].record()
     barrier()
     rollout_ms, train_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    epoch_ms = time_epoch_kernel(model, dev)
+    epoch_ms = time_epoch_kernel(model, dev, batch)
     peaks, peaks_src = measured_peaks()
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     tensor_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone
     flops = FLOPS[env_name]
     achieved = flops * steps_per_iter / (epoch_ms * 1e-3) / 1e12
-    default_cfg = (env_name, n_envs, n_steps) == ("point", N_ENVS, N_STEPS)
+    default_cfg = (env_name, n_envs, n_steps, batch) == ("point", N_ENVS, N_STEPS, BATCH)
     kp = 16 if OBS_DIM[env_name] + 1 <= 16 else 32
-    roofline = {"kernel": f"ppo_epoch_tc_kernel<{kp}> (one launch = one epoch = {steps_per_iter // BATCH} minibatch updates: "
+    roofline = {"kernel": f"ppo_epoch_tc_kernel<{kp}> (one launch = one epoch = {steps_per_iter // batch} minibatch updates: "
                           "tcgen05 forward/backward GEMMs, bulk-reduced gradient, clip, Adam)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES if default_cfg else None,
@@ -388,7 +390,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 policy+PPO", "data": "synthetic",
             "config": {"workload": workload_name(env_name, n_envs), "n_envs_per_gpu": n_envs, "n_steps": n_steps,
-                       "batch_size": BATCH, "n_epochs": N_EPOCHS, "minibatches_per_epoch": steps_per_iter // BATCH,
+                       "batch_size": batch, "n_epochs": N_EPOCHS, "minibatches_per_epoch": steps_per_iter // batch,
                        "permutation": "device (mr_device_permutation, the PPO default)",
                        "parallelism": f"dp{world} (envs sharded, gradient all-reduce)",
                        "l2": f"no flush: every step rewrites its {steps_per_iter * 84 / 1e6:.0f} MB rollout working set and "
@@ -424,7 +426,7 @@ EPOCH_KERNEL_DRAM_BYTES = 143.1e6  # 138.6 MB read + 4.5 MB written (profiles/r0
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
-def time_epoch_kernel(model, dev):
+def time_epoch_kernel(model, dev, batch=BATCH):
     """Average duration of the epoch kernel alone, CUDA events on the launching stream.  Parameters
     and Adam state are restored afterwards (the launches are real updates)."""
     import torch
@@ -433,16 +435,16 @@ def time_epoch_kernel(model, dev):
     T, N = model.n_steps, model.env.num_envs
     saved = [t.clone() for t in (up.params, up.exp_avg, up.exp_avg_sq, up.step)]
     perm = torch.randperm(T * N, device=dev, dtype=torch.int64)
-    stats = up.adv_stats(b["advantages"], perm, BATCH, N, T)
+    stats = up.adv_stats(b["advantages"], perm, batch, N, T)
     up.pack(b)
     for _ in range(2):
-        up.train_epoch_fused(None, perm, stats, BATCH, N, T)
+        up.train_epoch_fused(None, perm, stats, batch, N, T)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     e0.record()
     for _ in range(reps):
-        up.train_epoch_fused(None, perm, stats, BATCH, N, T)
+        up.train_epoch_fused(None, perm, stats, batch, N, T)
     e1.record()
     torch.cuda.synchronize(dev)
     for t, sv in zip((up.params, up.exp_avg, up.exp_avg_sq, up.step), saved):

@@ -557,18 +557,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                 const float val[4] = {mine.x, mine.y, mine.z, mine.w};
                 const unsigned seq = E.seq0 + (unsigned)m + 1u;
                 const int slot = seq & 1u;
-                const size_t p = 4 * (size_t)my_quad;
+                // Inbox of (slot, source rank): two regions of nq 16-byte entries, {packet 0, packet 1} and
+                // {packet 2, packet 3} of every quad, so that ONE 16-byte store per thread and region makes a warp's
+                // push a contiguous range (a few full NVLink writes instead of a 32-byte sector per packet: at 8 ranks
+                // the scalar form sent 79 000 sector-sized writes per minibatch and rank).  Every 8-byte packet still
+                // carries its own tag, so the 16-byte stores need not arrive atomically.
+                unsigned long long pk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned long long pkt = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(val[e]);
-                    for (int r = 0; r < E.X.world; ++r)
-                        if (r != E.X.rank)
-                            __stcg(E.X.peer_inbox[r] + ((size_t)slot * E.X.world + E.X.rank) * acc_floats + p + e, pkt);
-                }
+                for (int e = 0; e < 4; ++e) pk[e] = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(val[e]);
+                const size_t ent = ((size_t)slot * E.X.world + E.X.rank) * acc_floats + 2 * (size_t)my_quad;
+                for (int r = 0; r < E.X.world; ++r)
+                    if (r != E.X.rank) {
+                        unsigned long long* dst = E.X.peer_inbox[r] + ent;
+                        asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(pk[0]), "l"(pk[1]) : "memory");
+                        asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * (size_t)nq), "l"(pk[2]), "l"(pk[3]) : "memory");
+                    }
                 // pull: the four packets of every peer, four peers per wave of 16-byte loads; payloads wait in
                 // shared memory.  A peer that never delivers (dead rank) ends the wait after ~4 s: the flag is
                 // raised and the epoch finishes on what arrived, so the GPU is released instead of hanging.
-                const unsigned long long* src0 = E.X.inbox + (size_t)slot * E.X.world * acc_floats + p;
+                const unsigned long long* src0 = E.X.inbox + (size_t)slot * E.X.world * acc_floats + 2 * (size_t)my_quad;
                 unsigned pending = ((1u << E.X.world) - 1u) & ~(1u << E.X.rank);
                 long long t0 = 0;
                 unsigned spins = 0;
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                             if (pending >> r & 1u) {
                                 const unsigned long long* q = src0 + (size_t)r * acc_floats;
                                 asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[k].x), "=l"(lo[k].y) : "l"(q) : "memory");
-                                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(hi[k].x), "=l"(hi[k].y) : "l"(q + 2) : "memory");
+                                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(hi[k].x), "=l"(hi[k].y) : "l"(q + 2 * (size_t)nq) : "memory");
                             }
                         }
 #pragma unroll
