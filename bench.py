@@ -422,7 +422,7 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 
 # dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
-EPOCH_KERNEL_DRAM_BYTES = 143.1e6  # 138.6 MB read + 4.5 MB written (profiles/r02_ncu_full.txt)
+EPOCH_KERNEL_DRAM_BYTES = 158.05e6  # 154.2 MB read + 3.9 MB written (profiles/r02_ncu_full.txt)
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 

@@ -259,6 +259,12 @@ int mr_device_permutations(uint64_t seed, const uint64_t* h_stream_ids, int coun
  * mr_ppo_epoch_fused then takes perm = NULL and rows = the epoch's row of `rows`. */
 int mr_ppo_prepare_epochs(const float* adv, const int64_t* perm, int n_epochs, int64_t n_samples, int64_t batch_size,
                           int64_t N, int64_t T, double* stats, int32_t* rows, void* stream);
+/* The same with the device index streams of mr_device_permutations(seed, h_stream_ids, n_epochs, N * T), generated
+ * on the fly: rows [n_epochs][N * T] and stats come out exactly as from the two calls, but the int64 permutations
+ * are never written (two launches per update). */
+int mr_ppo_prepare_epochs_device(uint64_t seed, const uint64_t* h_stream_ids, int n_epochs, const float* adv,
+                                 int64_t n_samples, int64_t batch_size, int64_t N, int64_t T, double* stats,
+                                 int32_t* rows, void* stream);
 
 /* Host-side minibatch index stream (no device work): out[0..n) <- a uniformly random permutation
  * of 0..n-1, a pure function of (seed, stream).  Replaces, for throughput runs, the

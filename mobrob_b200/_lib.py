@@ -63,6 +63,7 @@ _SIGNATURES = {
     "mr_device_permutation": (c_int, [c_uint64, c_uint64, c_int64, _P, _P]),
     "mr_device_permutations": (c_int, [c_uint64, _P, c_int, c_int64, _P, _P]),
     "mr_ppo_prepare_epochs": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "mr_ppo_prepare_epochs_device": (c_int, [c_uint64, _P, c_int, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     "mr_host_permutation": (c_int, [c_uint64, c_uint64, c_int64, _P]),
     "mr_adam_step": (c_int, [_P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float,
                              _P, _P]),

@@ -387,6 +387,59 @@ __global__ void __launch_bounds__(256) device_perm_kernel(int64_t* __restrict__ 
     out[(int64_t)blockIdx.y * n + i] = (int64_t)x;
 }
 
+// The device index stream straight to what the epoch kernel consumes: rows[e][i] = buffer row (t * N + n) of
+// the sample P_e(i) = n * T + t.  No int64 permutation is materialised (97 MB per update at the bench size).
+__global__ void __launch_bounds__(256) device_rows_kernel(int32_t* __restrict__ rows, int64_t n, int64_t N, int64_t T,
+                                                          PermKeys Ks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PermKey& K = Ks.k[blockIdx.y];
+    uint32_t x = (uint32_t)i;
+    do { x = perm_feistel(x, K); } while ((int64_t)x >= n);
+    const unsigned env = x / (unsigned)T, t = x - env * (unsigned)T;
+    rows[(int64_t)blockIdx.y * n + i] = (int32_t)((int64_t)t * N + env);
+}
+
+// adv_stats_kernel on buffer rows (several epochs per launch: block b -> minibatch b % n_mb of epoch b / n_mb)
+__global__ void __launch_bounds__(1024)
+adv_stats_rows_kernel(const float* __restrict__ adv, const int32_t* __restrict__ rows, int64_t n_samples, int64_t batch,
+                      double* __restrict__ stats, int n_mb) {
+    rows += (int64_t)(blockIdx.x / n_mb) * n_samples;
+    stats += (int64_t)(blockIdx.x / n_mb) * n_mb * 3;
+    const int64_t mb = blockIdx.x % n_mb;
+    const int64_t s0 = mb * batch, s1 = min(n_samples, s0 + batch);
+    double s = 0.0, q = 0.0;
+    constexpr int U = 4;   // independent gathers in flight per thread
+    for (int64_t i0 = s0 + threadIdx.x; i0 < s1; i0 += (int64_t)U * blockDim.x) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            a[u] = i < s1 ? __ldg(adv + __ldg(rows + i)) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s += (double)a[u];
+            q += (double)a[u] * (double)a[u];
+        }
+    }
+    __shared__ double sh[2][32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0, tq = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+        stats[3 * mb] = ts;
+        stats[3 * mb + 1] = tq;
+        stats[3 * mb + 2] = (double)(s1 - s0);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Persistent epoch kernel: every minibatch of one epoch in ONE cooperative launch (one CTA per SM).
 // Per minibatch: [stage parameters] -> forward/backward (grad_minibatch) -> grid barrier ->
@@ -777,6 +830,24 @@ int mr_ppo_prepare_epochs(const float* adv, const int64_t* perm, int n_epochs, i
     adv_stats_kernel<<<n_mb * n_epochs, 1024, 0, s>>>(adv, perm, n_samples, batch_size, N, T, stats, n_mb);
     MR_CHECK_LAUNCH();
     perm_to_rows_kernel<<<ceil_div(n_samples * n_epochs, 256), 256, 0, s>>>(perm, n_samples * n_epochs, N, T, rows);
+    MR_CHECK_LAUNCH();
+    return MR_OK;
+}
+
+// mr_device_permutations + mr_ppo_prepare_epochs in two launches, without materialising the int64 permutations.
+int mr_ppo_prepare_epochs_device(uint64_t seed, const uint64_t* h_stream_ids, int n_epochs, const float* adv,
+                                 int64_t n_samples, int64_t batch_size, int64_t N, int64_t T, double* stats,
+                                 int32_t* rows, void* stream) {
+    MR_REQUIRE(adv && h_stream_ids && stats && rows, "NULL argument");
+    MR_REQUIRE(n_samples > 0 && n_samples == N * T && n_samples < (int64_t(1) << 31), "n_samples must equal N * T (< 2^31)");
+    MR_REQUIRE(n_epochs > 0 && n_epochs <= MAX_PERMS && batch_size > 0, "1 to 32 epochs per call");
+    cudaStream_t s = (cudaStream_t)stream;
+    PermKeys Ks{};
+    for (int e = 0; e < n_epochs; ++e) Ks.k[e] = make_perm_key(seed, h_stream_ids[e], n_samples);
+    device_rows_kernel<<<dim3(ceil_div(n_samples, 256), n_epochs), 256, 0, s>>>(rows, n_samples, N, T, Ks);
+    MR_CHECK_LAUNCH();
+    const int n_mb = ceil_div(n_samples, batch_size);
+    adv_stats_rows_kernel<<<n_mb * n_epochs, 1024, 0, s>>>(adv, rows, n_samples, batch_size, stats, n_mb);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }

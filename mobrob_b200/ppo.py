@@ -327,19 +327,11 @@ class PPO:
         _lib.check(self.lib.mr_device_permutation(int(self.seed or 0), key, n, out.data_ptr(), self._stream()))
         return out
 
-    def _device_permutations(self, n):
-        """All epochs' index streams of this update in one launch: [n_epochs, n] int64 (mr_device_permutations)."""
-        import ctypes
-
-        E = self.n_epochs
-        if getattr(self, "_dperm_all", None) is None or self._dperm_all.shape != (E, n):
-            self._dperm_all = torch.empty((E, n), dtype=torch.int64, device=self.device)
+    def _stream_ids(self):
+        """Keys of this update's device index streams, one per epoch: (rank, update count, epoch)."""
         d = _dist()
         rank = d.get_rank() if d is not None else 0
-        keys = (ctypes.c_uint64 * E)(*[(rank << 48) ^ (self._train_count << 16) ^ e for e in range(E)])
-        _lib.check(self.lib.mr_device_permutations(int(self.seed or 0), keys, E, n, self._dperm_all.data_ptr(),
-                                                   self._stream()))
-        return self._dperm_all
+        return [(rank << 48) ^ (self._train_count << 16) ^ e for e in range(self.n_epochs)]
 
     def train(self, perms=None):
         """PPO.train: n_epochs passes of minibatch updates.  perms: optional list of int64 index
@@ -369,8 +361,7 @@ class PPO:
         if self.update_mode == "fused" and perms is None and self.permutation == "device" and self.n_epochs <= 32:
             # the whole update's index streams, advantage sums and row indices up front (3 launches and, with
             # several ranks, ONE all-reduce), then nothing but the epoch kernels back to back
-            perm_all = self._device_permutations(n)
-            stats_all, rows_all = up.prepare_epochs(b["advantages"], perm_all, B, N, T)
+            stats_all, rows_all = up.prepare_epochs_device(b["advantages"], int(self.seed or 0), self._stream_ids(), B, N, T)
             if d is not None:
                 flat, _ = sharding.allreduce_adv_stats(stats_all.view(-1, 3))
                 stats_all = flat.view(self.n_epochs, n_mb, 3)

@@ -117,6 +117,20 @@ class PpoUpdater:
                                                   stats.data_ptr(), self._rows_all.data_ptr(), self._stream()))
         return stats, self._rows_all
 
+    def prepare_epochs_device(self, adv: torch.Tensor, seed: int, stream_ids, batch_size: int, N: int, T: int):
+        """prepare_epochs for the device index streams (seed, stream_ids), generated on the fly."""
+        import ctypes
+
+        E, n = len(stream_ids), N * T
+        n_mb = (n + batch_size - 1) // batch_size
+        stats = torch.empty((E, n_mb, 3), dtype=torch.float64, device=self.device)
+        if getattr(self, "_rows_all", None) is None or self._rows_all.shape != (E, n):
+            self._rows_all = torch.empty((E, n), dtype=torch.int32, device=self.device)
+        keys = (ctypes.c_uint64 * E)(*stream_ids)
+        _lib.check(self.lib.mr_ppo_prepare_epochs_device(seed, keys, E, adv.data_ptr(), n, batch_size, N, T,
+                                                         stats.data_ptr(), self._rows_all.data_ptr(), self._stream()))
+        return stats, self._rows_all
+
     def train_epoch_fused(self, buf: dict | None, perm: torch.Tensor | None, stats: torch.Tensor, batch_size: int, N: int,
                           T: int, info: torch.Tensor | None = None, xchg=None, rows: torch.Tensor | None = None):
         """One cooperative launch for the whole epoch; xchg (PeerExchange) adds the in-kernel

@@ -75,3 +75,30 @@ def test_minibatches_are_well_mixed(cuda_lib):
         # no short-range structure: neighbours in the stream are far apart in the buffer
         assert np.median(np.abs(np.diff(p[:10000]))) > n / 8
     assert worst < 0.01
+
+
+def test_prepare_epochs_device_equals_the_two_step_form(cuda_lib):
+    """mr_ppo_prepare_epochs_device (index streams generated on the fly) == mr_device_permutations followed by
+    mr_ppo_prepare_epochs: same buffer rows bit for bit, same per-minibatch advantage sums; and the rows are
+    what numpy makes of the restated permutation."""
+    import ctypes
+
+    from mobrob_b200.updater import PpoUpdater
+
+    N, T, B, E, seed = 37, 64, 300, 3, 11
+    n = N * T
+    up = PpoUpdater(14, torch.device("cuda", 0))
+    adv = torch.randn((T, N), device="cuda")
+    ids = [(2 << 48) ^ (7 << 16) ^ e for e in range(E)]
+    perms = torch.empty((E, n), dtype=torch.int64, device="cuda")
+    keys = (ctypes.c_uint64 * E)(*ids)
+    _lib.check(up.lib.mr_device_permutations(seed, keys, E, n, perms.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    stats_a, rows_a = up.prepare_epochs(adv, perms, B, N, T)
+    rows_a = rows_a.clone()
+    stats_b, rows_b = up.prepare_epochs_device(adv, seed, ids, B, N, T)
+    assert torch.equal(rows_a, rows_b)
+    np.testing.assert_allclose(stats_b.cpu().numpy(), stats_a.cpu().numpy(), rtol=1e-14)
+    for e in range(E):
+        p = perm_ref(seed, ids[e], n)
+        np.testing.assert_array_equal(perms[e].cpu().numpy(), p)
+        np.testing.assert_array_equal(rows_b[e].cpu().numpy(), (p % T) * N + p // T)
