@@ -60,6 +60,12 @@ int mr_env_state_dim(const mr_env* env); /* doubles per env in get/set_state */
  * BASELINE.json asks for 1e-5 state parity.  Default 1. */
 int mr_env_set_contacts(mr_env* env, int enabled);
 
+/* EnvWrapper.reset_init_space / reset_goal_space (wrapper.py:209-219) for every env of the batch: resets after
+ * this call draw the start position / the goal from the new boxes (defaults: MujocoGoalEnv.get_init_space /
+ * get_goal_space, wrapper.py:250-264).  h_init, h_goal: (low x, low y, high x, high y) float32 in host memory;
+ * either may be NULL (unchanged).  Each env keeps its own random stream. */
+int mr_env_set_spaces(mr_env* env, const float* h_init, const float* h_goal, void* stream);
+
 /* EnvWrapper.seed (wrapper.py:95-107) for every env: the two gymnasium Box streams
  * (init_space -> PCG64(SeedSequence(s)), goal_space -> PCG64(SeedSequence(s + 1))) arrive as
  * raw PCG64 words [N][4] = (state_hi, state_lo, inc_hi, inc_lo); engine_seed [N] is

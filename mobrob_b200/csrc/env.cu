@@ -401,7 +401,34 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
         e->car.carve(e->slab, n_envs);
         e->carK = make_car_consts();
     }
+    // MujocoGoalEnv.get_init_space / get_goal_space (wrapper.py:250-264): extents / 2 and extents
+    const float spaces[8] = {-1.f, -1.f, 1.f, 1.f, -2.f, -2.f, 2.f, 2.f};
+    cudaMemcpy(const_cast<float*>(kind == MR_ENV_POINT ? e->point.cold.spaces : e->car.cold.spaces), spaces,
+               sizeof(spaces), cudaMemcpyHostToDevice);
     *out = e;
+    return MR_OK;
+}
+
+static const EnvCold& cold_of(const mr_env* env) {
+    return env->kind == MR_ENV_POINT ? env->point.cold : env->car.cold;
+}
+
+// EnvWrapper.reset_init_space / reset_goal_space (wrapper.py:209-219) for every env of the batch: later resets draw
+// from the new boxes.  Each env keeps its own random stream (the reference swaps in the new Box object, whose
+// generator EnvWrapper.seed re-seeds at the next seeded reset).  h_init / h_goal: (low x, low y, high x, high y) in
+// host memory, either may be NULL (unchanged).
+int mr_env_set_spaces(mr_env* env, const float* h_init, const float* h_goal, void* stream) {
+    MR_REQUIRE(env, "env is NULL");
+    DeviceGuard guard(env->device);
+    float* d = const_cast<float*>(cold_of(env).spaces);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int k = 0; k < 2; ++k) {
+        const float* h = k == 0 ? h_init : h_goal;
+        if (!h) continue;
+        MR_REQUIRE(h[0] <= h[2] && h[1] <= h[3], "space bounds: low must not exceed high");
+        MR_CUDA(cudaMemcpyAsync(d + 4 * k, h, 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    MR_CUDA(cudaStreamSynchronize(s));  // host buffers may be freed by the caller on return
     return MR_OK;
 }
 
@@ -424,9 +451,6 @@ int mr_env_set_contacts(mr_env* env, int enabled) {
     return MR_OK;
 }
 
-static const EnvCold& cold_of(const mr_env* env) {
-    return env->kind == MR_ENV_POINT ? env->point.cold : env->car.cold;
-}
 
 int mr_env_seed(mr_env* env, const uint64_t* h_pcg_init, const uint64_t* h_pcg_goal,
                 const int64_t* h_engine_seed, void* stream) {

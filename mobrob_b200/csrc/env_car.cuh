@@ -31,7 +31,7 @@ struct CarSoA {
     static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
     static size_t slab_bytes(int64_t n) {
         return align_up(n * 8 * car::NSTATE) + 2 * align_up(n * 8) + align_up(n * 4) + align_up(n * 8) +
-               2 * align_up(n * 32) + 4 * align_up(n * 8);
+               2 * align_up(n * 32) + 4 * align_up(n * 8) + align_up(32);
     }
     void carve(void* slab, int64_t n_) {
         n = n_;
@@ -47,6 +47,7 @@ struct CarSoA {
         cold.body_xy = (float2*)take(n * 8);
         cold.psi0 = (double*)take(n * 8);
         cold.counts = (int32_t*)take(n * 8);
+        cold.spaces = (const float*)take(32);
     }
     __device__ __forceinline__ CarHot load(int64_t i) const {
         CarHot h;
@@ -76,8 +77,8 @@ __device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool
         int64_t seed = cold.engine_seed[i] + 1;
         cold.engine_seed[i] = seed;
         Pcg64 g = load_pcg(cold.pcg_init, i);
-        float x = (float)g.uniform(-1.0, 1.0);
-        float y = (float)g.uniform(-1.0, 1.0);
+        float x = (float)g.uniform((double)cold.spaces[0], (double)cold.spaces[2]);
+        float y = (float)g.uniform((double)cold.spaces[1], (double)cold.spaces[3]);
         store_pcg(cold.pcg_init, i, g);
         double heading = engine_heading((uint32_t)seed);
         car::State& s = h.s;
@@ -95,8 +96,8 @@ __device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool
         cold.counts[2 * i + 1] += 1;
     }
     Pcg64 g = load_pcg(cold.pcg_goal, i);
-    h.gx = (float)g.uniform(-2.0, 2.0);
-    h.gy = (float)g.uniform(-2.0, 2.0);
+    h.gx = (float)g.uniform((double)cold.spaces[4], (double)cold.spaces[6]);
+    h.gy = (float)g.uniform((double)cold.spaces[5], (double)cold.spaces[7]);
     store_pcg(cold.pcg_goal, i, g);
     h.elapsed = 0;
     h.ep_ret = 0.0;

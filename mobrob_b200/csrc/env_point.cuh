@@ -24,6 +24,8 @@ struct EnvCold {
     float2* body_xy;       // [N] model.body_pos[robot][:2]
     double* psi0;          // [N] start heading (body quat)
     int32_t* counts;       // [N][2] (#resets, #full resets)
+    const float* spaces;   // [8] init low (x, y), init high, goal low, goal high: EnvWrapper.init_space / goal_space
+                           // (defaults wrapper.py:250-264; reset_init_space / reset_goal_space, wrapper.py:209-219)
 };
 
 struct PointHot {
@@ -62,8 +64,9 @@ __device__ inline void point_reset(PointHot& h, const EnvCold& cold, int64_t i, 
         int64_t seed = cold.engine_seed[i] + 2;
         cold.engine_seed[i] = seed;
         Pcg64 g = load_pcg(cold.pcg_init, i);
-        float x = (float)g.uniform(-1.0, 1.0);  // init_space = extents / 2 (wrapper.py:250-256)
-        float y = (float)g.uniform(-1.0, 1.0);
+        // init_space.sample(): default extents / 2 (wrapper.py:250-256); float32 bounds, float64 arithmetic
+        float x = (float)g.uniform((double)cold.spaces[0], (double)cold.spaces[2]);
+        float y = (float)g.uniform((double)cold.spaces[1], (double)cold.spaces[3]);
         store_pcg(cold.pcg_init, i, g);
         double heading = engine_heading((uint32_t)seed);
         h.d.px = (double)x;
@@ -76,8 +79,8 @@ __device__ inline void point_reset(PointHot& h, const EnvCold& cold, int64_t i, 
         cold.counts[2 * i + 1] += 1;
     }
     Pcg64 g = load_pcg(cold.pcg_goal, i);
-    h.gx = (float)g.uniform(-2.0, 2.0);  // goal_space = extents (wrapper.py:258-264)
-    h.gy = (float)g.uniform(-2.0, 2.0);
+    h.gx = (float)g.uniform((double)cold.spaces[4], (double)cold.spaces[6]);  // goal_space: default extents (wrapper.py:258-264)
+    h.gy = (float)g.uniform((double)cold.spaces[5], (double)cold.spaces[7]);
     store_pcg(cold.pcg_goal, i, g);
     h.elapsed = 0;
     h.ep_ret = 0.0;

@@ -35,6 +35,7 @@ struct PointState {
         b += align_up(n * 8);       // body_xy
         b += align_up(n * 8);       // psi0
         b += align_up(n * 8);       // counts
+        b += align_up(32);          // spaces
         return b;
     }
     void carve(void* slab, int64_t n_) {
@@ -47,6 +48,7 @@ struct PointState {
         cold.body_xy = (float2*)take(n * 8);
         cold.psi0 = (double*)take(n * 8);
         cold.counts = (int32_t*)take(n * 8);
+        cold.spaces = (const float*)take(32);
     }
 
     // address of env i's 8-byte slot in field 0 of its tile; the other fields are at + F_*

@@ -46,6 +46,9 @@ class GpuVecEnv:
         self.state_dim = int(self.lib.mr_env_state_dim(h))
         self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,), np.float32)
         self.action_space = Box(-1.0, 1.0, (2,), np.float32)
+        # MujocoGoalEnv.get_init_space / get_goal_space (wrapper.py:250-264)
+        self.init_space = Box(np.array([-1.0, -1.0], np.float32), np.array([1.0, 1.0], np.float32), dtype=np.float32)
+        self.goal_space = Box(np.array([-2.0, -2.0], np.float32), np.array([2.0, 2.0], np.float32), dtype=np.float32)
         N, O, dev = self.num_envs, self.obs_dim, self.device
         self.obs = torch.zeros((N, O), dtype=torch.float32, device=dev)
         self.rew = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -142,6 +145,22 @@ class GpuVecEnv:
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
+
+    # -- EnvWrapper.reset_init_space / reset_goal_space (wrapper.py:209-219) for the whole batch ------------------
+    def _set_spaces(self):
+        init = np.concatenate([self.init_space.low, self.init_space.high]).astype(np.float32)
+        goal = np.concatenate([self.goal_space.low, self.goal_space.high]).astype(np.float32)
+        _lib.check(self.lib.mr_env_set_spaces(self._h, init.ctypes.data, goal.ctypes.data, self._stream()))
+
+    def reset_init_space(self, init_space):
+        """Later full resets place the robot in `init_space` (a 2-d Box).  Every env keeps its own random stream."""
+        self.init_space = init_space
+        self._set_spaces()
+
+    def reset_goal_space(self, goal_space):
+        """Later resets draw the goal from `goal_space` (a 2-d Box)."""
+        self.goal_space = goal_space
+        self._set_spaces()
 
     def set_contacts(self, enabled: bool):
         """car only: switch the floor contacts off for contact-free parity trajectories."""

@@ -47,6 +47,17 @@ class GoalVecOracle:
         self.n_resets = np.zeros(self.n, dtype=np.int64)
         self.n_full = np.zeros(self.n, dtype=np.int64)
 
+    def reset_init_space(self, low, high):
+        """EnvWrapper.reset_init_space (wrapper.py:209-213) for every env; the streams continue (the batched env's
+        convention: the reference swaps in the new Box object, re-seeded by EnvWrapper.seed at the next seeded reset)."""
+        for b in self.init_rng:
+            b.low, b.high = np.asarray(low, np.float32), np.asarray(high, np.float32)
+
+    def reset_goal_space(self, low, high):
+        """EnvWrapper.reset_goal_space (wrapper.py:215-219)."""
+        for b in self.goal_rng:
+            b.low, b.high = np.asarray(low, np.float32), np.asarray(high, np.float32)
+
     # ------------------------------------------------------------------------
     def reached(self):
         p = self.body.pos()

@@ -170,3 +170,35 @@ def test_point_fast_spin_and_large_heading_paths(cuda_lib):
     ref = body.state_vector()
     err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
     assert err.max() < RTOL, err.max()
+
+
+@pytest.mark.parametrize("env_name", ["point", "car"])
+def test_reset_spaces_of_the_batched_env(cuda_lib, env_name):
+    """EnvWrapper.reset_init_space / reset_goal_space (wrapper.py:209-219) on the batched env: resets after the
+    call draw start positions and goals from the new boxes, from each env's own continuing stream -- bit-exact
+    against the oracle's streams (numpy PCG64)."""
+    from mobrob_b200 import GpuVecEnv
+    from mobrob_b200.spaces import Box
+    from oracle import car_oracle as co
+
+    n, seed = 40, 9
+    body = po.PointBody(n) if env_name == "point" else co.CarBody(n)
+    env = GpuVecEnv(env_name, n, seed=seed, time_limit=7, terminate_on_goal=True)
+    ora = GoalVecOracle(body, seed=seed, time_limit=7, terminate_on_goal=True)
+    env.reset(); ora.reset()
+    lo_i, hi_i = np.array([0.5, -0.25], np.float32), np.array([0.75, 0.0], np.float32)
+    lo_g, hi_g = np.array([-2.0, 1.5], np.float32), np.array([-1.75, 2.0], np.float32)
+    env.reset_init_space(Box(lo_i, hi_i, dtype=np.float32)); ora.reset_init_space(lo_i, hi_i)
+    env.reset_goal_space(Box(lo_g, hi_g, dtype=np.float32)); ora.reset_goal_space(lo_g, hi_g)
+    a = np.zeros((n, 2), np.float32)
+    for t in range(8):          # the 7-step time limit truncates every env once: full resets into the new boxes
+        o, r, d, _ = env.step(a)
+        o_ref, r_ref, d_ref, _ = ora.step(a)
+        np.testing.assert_array_equal(d, d_ref)
+    st = env.get_state().cpu().numpy()
+    goal_slot = 11 if env_name == "point" else 26
+    np.testing.assert_array_equal(st[:, goal_slot:goal_slot + 2].astype(np.float32), ora.goal)
+    pos = env.get_pos().cpu().numpy()
+    np.testing.assert_allclose(pos, ora.body.pos(), rtol=1e-5, atol=1e-6)
+    assert (pos[:, 0] >= 0.45).all() and (pos[:, 0] <= 0.8).all() and (pos[:, 1] >= -0.3).all() and (pos[:, 1] <= 0.05).all()
+    assert (ora.goal[:, 0] <= -1.75).all() and (ora.goal[:, 1] >= 1.5).all()
