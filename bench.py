@@ -323,7 +323,7 @@ def run_ours(args):
                 "step_share": {"rollout_ms": rollout_ms, "update_ms": train_ms,
                                "epoch_kernel_ms_x_epochs": epoch_ms * N_EPOCHS}}
     env_roof = None
-    if default_cfg and not args.no_extras:
+    if default_cfg and not args.no_extras and world == 1:
         env_roof = time_env_step_kernel(dev, peaks)
 
     # ---- e2e: the public API, PPOCtrl.learn(), as a user calls it: host loop, logger and episode-buffer
@@ -346,7 +346,7 @@ def run_ours(args):
     sampler.active = False
     d2h = EP_D2H_BYTES + 12 * 4
     e2e_host = None
-    if not args.no_extras and env_name == "point":
+    if not args.no_extras and env_name == "point" and world == 1:
         # SB3's own semantics for RolloutBuffer.get: permutations drawn on the HOST (thread pool, one iteration
         # ahead) and copied from pinned memory every epoch
         model.permutation = "pool"
