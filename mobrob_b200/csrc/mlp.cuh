@@ -54,8 +54,24 @@ struct SmemW {
 
 __host__ __device__ inline int smem_w_floats(int O) { return 128 * O + 8192 + 128 + 128 + 192 + 4 + 4; }
 
+// One weight matrix of both towers, [64][K] row-major in global memory -> the packed image dst[k][lane]{4}.
+// A warp reads an 8-row x 4-column patch per pass (8 full sectors; the first form of this loop read one
+// column of 32 rows, i.e. 32 sectors for 128 bytes, and the L1's sector rate -- not latency -- made staging
+// 40 us of a 45 us policy_forward launch) and scatters it with 4-way bank conflicts at worst.
+__device__ __forceinline__ void stage_matrix(float* dst, const float* __restrict__ pi_w, const float* __restrict__ vf_w, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int kb_n = (K + 3) >> 2;
+    const int n_items = 2 * 8 * kb_n;   // (tower, block of 8 rows, block of 4 columns)
+#pragma unroll 8
+    for (int it = warp; it < n_items; it += n_warps) {
+        const int kb = it % kb_n, ub = (it / kb_n) & 7, t = it / (8 * kb_n);
+        const int u = 8 * ub + (lane >> 2), k = 4 * kb + (lane & 3);
+        if (k < K) dst[k * 128 + (u & 31) * 4 + (u >> 5) + 2 * t] = __ldcg((t ? vf_w : pi_w) + u * K + k);
+    }
+}
+
 // All threads of the block cooperate; caller must __syncthreads() afterwards.  Loads go through
-// L2 (ld.cg): the persistent epoch kernel re-stages parameters another CTA has just updated.
+// L2 (ld.cg): parameters may have been updated by a kernel that ran just before on another SM.
 __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ params, int O) {
     const ParamLayout L = make_layout(O);
     float* w1 = smem;
@@ -65,20 +81,8 @@ __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ par
     float* hw = b2 + 128;
     float* hb = hw + 192;
     float* ls = hb + 4;
-#pragma unroll 7
-    for (int idx = threadIdx.x; idx < 128 * O; idx += blockDim.x) {
-        int k = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
-        int u = lane + ((j & 1) ? 32 : 0);
-        int base = (j & 2) ? L.vw1 : L.pw1;
-        w1[idx] = __ldcg(params + base + u * O + k);
-    }
-#pragma unroll 8
-    for (int idx = threadIdx.x; idx < 8192; idx += blockDim.x) {
-        int k = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
-        int u = lane + ((j & 1) ? 32 : 0);
-        int base = (j & 2) ? L.vw2 : L.pw2;
-        w2[idx] = __ldcg(params + base + u * HID + k);
-    }
+    stage_matrix(w1, params + L.pw1, params + L.vw1, O);
+    stage_matrix(w2, params + L.pw2, params + L.vw2, HID);
     for (int idx = threadIdx.x; idx < 128; idx += blockDim.x) {
         int lane = idx >> 2, j = idx & 3;
         int u = lane + ((j & 1) ? 32 : 0);
@@ -91,102 +95,6 @@ __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ par
         hb[threadIdx.x] = threadIdx.x < 2 ? __ldcg(params + L.ab + threadIdx.x)
                                           : (threadIdx.x == 2 ? __ldcg(params + L.cb) : 0.f);
         ls[threadIdx.x] = threadIdx.x < 2 ? __ldcg(params + L.logstd + threadIdx.x) : 0.f;
-    }
-    SmemW W;
-    W.w1p = reinterpret_cast<const float4*>(w1);
-    W.w2p = reinterpret_cast<const float4*>(w2);
-    W.b1p = reinterpret_cast<const float4*>(b1);
-    W.b2p = reinterpret_cast<const float4*>(b2);
-    W.headw = hw;
-    W.headb = hb;
-    W.logstd = ls;
-    return W;
-}
-
-// Raw (row-padded) image of the flat parameter vector in shared memory: matrices keep their
-// [out][in] order but with row stride in + 1, so that the packing pass can read a column of 32
-// rows without bank conflicts.  Used by the PPO kernels, which re-stage parameters every
-// minibatch: one coalesced pass over global memory, then a shared-to-shared repack.
-struct RawLayout {
-    int pw1, vw1, pw2, vw2, misc, total;  // misc: logstd pb1 pb2 vb1 vb2 aw ab cw cb (unpadded)
-};
-__host__ __device__ inline RawLayout make_raw_layout(int O) {
-    RawLayout R;
-    R.pw1 = 0;
-    R.vw1 = R.pw1 + HID * (O + 1);
-    R.pw2 = R.vw1 + HID * (O + 1);
-    R.vw2 = R.pw2 + HID * (HID + 1);
-    R.misc = R.vw2 + HID * (HID + 1);
-    R.total = R.misc + ACT + 4 * HID + ACT * HID + ACT + HID + 1;
-    return R;
-}
-
-// global -> raw: consecutive threads read consecutive floats (ld.cg, see stage_weights).
-__device__ inline void stage_raw(float* raw, const float* params, int O) {
-    const ParamLayout L = make_layout(O);
-    const RawLayout R = make_raw_layout(O);
-    const int m_logstd = R.misc, m_pb1 = m_logstd + ACT, m_pb2 = m_pb1 + HID, m_vb1 = m_pb2 + HID,
-              m_vb2 = m_vb1 + HID, m_aw = m_vb2 + HID, m_ab = m_aw + ACT * HID, m_cw = m_ab + ACT,
-              m_cb = m_cw + HID;
-#pragma unroll 8
-    for (int i = threadIdx.x; i < L.total; i += blockDim.x) {
-        const float v = __ldcg(params + i);
-        int d;
-        if (i < L.pw1) d = m_logstd + i;
-        else if (i < L.pb1) { int r = i - L.pw1, row = r / O; d = R.pw1 + row * (O + 1) + (r - row * O); }
-        else if (i < L.pw2) d = m_pb1 + (i - L.pb1);
-        else if (i < L.pb2) { int r = i - L.pw2; d = R.pw2 + (r >> 6) * (HID + 1) + (r & 63); }
-        else if (i < L.vw1) d = m_pb2 + (i - L.pb2);
-        else if (i < L.vb1) { int r = i - L.vw1, row = r / O; d = R.vw1 + row * (O + 1) + (r - row * O); }
-        else if (i < L.vw2) d = m_vb1 + (i - L.vb1);
-        else if (i < L.vb2) { int r = i - L.vw2; d = R.vw2 + (r >> 6) * (HID + 1) + (r & 63); }
-        else if (i < L.aw) d = m_vb2 + (i - L.vb2);
-        else if (i < L.ab) d = m_aw + (i - L.aw);
-        else if (i < L.cw) d = m_ab + (i - L.ab);
-        else if (i < L.cb) d = m_cw + (i - L.cw);
-        else d = m_cb;
-        raw[d] = v;
-    }
-}
-
-// raw -> packed images (forward pack as in stage_weights, plus the backward pack of W2:
-// w2b[u][lane] = {pi W2[u][l], pi W2[u][l+32], vf W2[u][l], vf W2[u][l+32]}).
-__device__ inline SmemW pack_from_raw(float* smem, float* w2b, const float* raw, int O) {
-    const RawLayout R = make_raw_layout(O);
-    const int m_logstd = R.misc, m_pb1 = m_logstd + ACT, m_pb2 = m_pb1 + HID, m_vb1 = m_pb2 + HID,
-              m_vb2 = m_vb1 + HID, m_aw = m_vb2 + HID, m_ab = m_aw + ACT * HID, m_cw = m_ab + ACT,
-              m_cb = m_cw + HID;
-    float* w1 = smem;
-    float* w2 = w1 + 128 * O;
-    float* b1 = w2 + 8192;
-    float* b2 = b1 + 128;
-    float* hw = b2 + 128;
-    float* hb = hw + 192;
-    float* ls = hb + 4;
-    for (int idx = threadIdx.x; idx < 128 * O; idx += blockDim.x) {
-        int k = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
-        int u = lane + ((j & 1) ? 32 : 0);
-        w1[idx] = raw[((j & 2) ? R.vw1 : R.pw1) + u * (O + 1) + k];
-    }
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < 8192; idx += blockDim.x) {
-        int a = idx >> 7, r = idx & 127, lane = r >> 2, j = r & 3;
-        int b = lane + ((j & 1) ? 32 : 0);
-        const int base = (j & 2) ? R.vw2 : R.pw2;
-        w2[idx] = raw[base + b * (HID + 1) + a];   // forward: a = input k, b = output unit
-        w2b[idx] = raw[base + a * (HID + 1) + b];  // backward: a = output unit u, b = input k
-    }
-    for (int idx = threadIdx.x; idx < 128; idx += blockDim.x) {
-        int lane = idx >> 2, j = idx & 3;
-        int u = lane + ((j & 1) ? 32 : 0);
-        b1[idx] = raw[((j & 2) ? m_vb1 : m_pb1) + u];
-        b2[idx] = raw[((j & 2) ? m_vb2 : m_pb2) + u];
-    }
-    for (int idx = threadIdx.x; idx < 192; idx += blockDim.x)
-        hw[idx] = idx < 128 ? raw[m_aw + idx] : raw[m_cw + idx - 128];
-    if (threadIdx.x < 4) {
-        hb[threadIdx.x] = threadIdx.x < 2 ? raw[m_ab + threadIdx.x] : (threadIdx.x == 2 ? raw[m_cb] : 0.f);
-        ls[threadIdx.x] = threadIdx.x < 2 ? raw[m_logstd + threadIdx.x] : 0.f;
     }
     SmemW W;
     W.w1p = reinterpret_cast<const float4*>(w1);

@@ -13,8 +13,17 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
                       float* __restrict__ logp, float* __restrict__ val, int64_t n,
                       const uint8_t* __restrict__ mask) {
     extern __shared__ __align__(16) float smem[];
-    SmemW W = stage_weights(smem, params, O);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (mask) {
+        // masked call (V(terminal_observation) of the rollout's time-out bootstrap): truncations are rare, so a block
+        // first looks whether any of its samples is flagged and leaves without staging the parameters if none is
+        bool any = false;
+        const int64_t per_pass = (int64_t)gridDim.x * PF_WARPS * PF_E;
+        for (int64_t s0 = ((int64_t)blockIdx.x * PF_WARPS + warp) * PF_E; s0 < n; s0 += per_pass)
+            any |= lane < PF_E && s0 + lane < n && mask[s0 + lane] != 0;
+        if (!__syncthreads_or(any)) return;
+    }
+    SmemW W = stage_weights(smem, params, O);
     float* obsT = smem + smem_w_floats(O) + warp * (MAX_OBS * PF_E + 128 * PF_E);
     float* hbuf = obsT + MAX_OBS * PF_E;
     __syncthreads();
@@ -24,8 +33,6 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
          tile += (int64_t)gridDim.x * PF_WARPS) {
         const int64_t s0 = tile * PF_E;
         const int rows = (int)min((int64_t)PF_E, n - s0);
-        // masked call (V(terminal_observation) of the rollout's time-out bootstrap): tiles without a flagged
-        // sample are skipped -- truncations are rare, so the launch costs next to nothing
         if (mask && !__any_sync(0xffffffffu, lane < rows && mask[s0 + lane] != 0)) continue;
         // rows of the tile are contiguous in obs: coalesced read, transposed into obsT[k][e]
         for (int idx = lane; idx < PF_E * O; idx += 32) {

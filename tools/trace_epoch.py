@@ -26,6 +26,12 @@ import bench
 from mobrob_b200 import _lib
 from mobrob_b200.rl_control.ppo import PPOCtrl
 
+world = int(os.environ.get("WORLD_SIZE", "1"))   # under torchrun: the exchange phases ("slice exchanged", "barrier B passed")
+rank = int(os.environ.get("RANK", "0"))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 cfg = dict(env_name="point", time_limit=1000, n_envs=bench.N_ENVS, vec_env_type="dummy", enable_gui=False, seed=0,
            ppo_kwargs=dict(policy="MlpPolicy", n_steps=bench.N_STEPS, n_epochs=1, ent_coef=0.05,
                            gae_lambda=0.5, batch_size=bench.BATCH, verbose=0, permutation="device"))
@@ -49,7 +55,7 @@ NAMES = {1: "mb start", 2: "mb start", 3: "partial reduced", 4: "barrier A passe
          19: "dZ1 stored+sync", 20: "tiles issued", 21: "dW1 done", 30: "gradient loaded", 31: "norm known",
          32: "slice summed", 33: "norm known", 34: "adam ctx", 35: "adam pass 1", 36: "adam pass 1 synced",
          37: "restaged"}
-for cta in (0, 1):
+for cta in (0, 1) if rank == 0 else ():
     n = lib.mr_trace_read(cta, buf.ctypes.data, 4096)
     ids = (buf[:n] >> np.uint64(56)).astype(int)
     ts = (buf[:n] & np.uint64((1 << 56) - 1)).astype(np.int64)
@@ -64,3 +70,6 @@ for cta in (0, 1):
     print("   -- mean per transition (ns), count")
     for (a, b), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         print(f"   {NAMES.get(a, a):26s} -> {NAMES.get(b, b):26s} {np.mean(v):9.0f} x{len(v):4d}  total {sum(v) / 1e3:8.1f} us")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
