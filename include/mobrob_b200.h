@@ -53,7 +53,19 @@ uint64_t mr_launch_count(void);
 int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int terminate_on_goal,
                   mr_env** out);
 void mr_env_destroy(mr_env* env);
-int mr_env_obs_dim(const mr_env* env);   /* point 14, car 26 (engine.py:420-567) */
+int mr_env_obs_dim(const mr_env* env);   /* point 14, car 26 (engine.py:420-567), plus the optional keys below */
+
+/* Optional keys of Engine.obs() (config flags engine.py:125,140-142; values engine.py:1179-1180, 1243-1248; the
+ * reference sets them through MujocoGoalEnv.get_robot_config, wrapper.py:235-240): bit 0 observe_goal_dist
+ * (exp(-|goal - pos|), 1 float), bit 1 observe_qpos (data.qpos: point 3, car 13), bit 2 observe_qvel (data.qvel:
+ * point 3, car 11), bit 3 observe_ctrl (data.ctrl, 2).  The row stays the concatenation in sorted key order
+ * (engine.py:1253-1259).  Call before the first reset; rows of obs / term_obs then have mr_env_obs_dim floats.
+ * MR_ERR_UNSUPPORTED for other bits (lidar, vision, hazards are outside the path). */
+#define MR_OBS_GOAL_DIST 1u
+#define MR_OBS_QPOS 2u
+#define MR_OBS_QVEL 4u
+#define MR_OBS_CTRL 8u
+int mr_env_set_obs_flags(mr_env* env, unsigned flags);
 int mr_env_state_dim(const mr_env* env); /* doubles per env in get/set_state */
 
 /* Test hook (car): 0 disables the floor contacts, giving the contact-free trajectories on which

@@ -97,9 +97,42 @@ point_step_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act,
     store_rows_coalesced(obs, s_obs, block_start, rows);
 }
 
+// Step with optional observation keys (EnvCfg::obs_flags != 0): same per-env logic, rows of obs_dim_ext floats
+// written row by row (this variant is not the measured hot path; the default configuration keeps the kernel above).
+__global__ void __launch_bounds__(STEP_THREADS)
+point_step_ext_kernel(PointState st, EnvCfg cfg, const float2* __restrict__ act, float* __restrict__ obs,
+                      float* __restrict__ rew, uint8_t* __restrict__ done, uint8_t* __restrict__ trunc,
+                      float* __restrict__ term_obs, double* __restrict__ ep_ret, int32_t* __restrict__ ep_len) {
+    const int64_t i = (int64_t)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    const int O = obs_dim_ext(point::OBS, 3, 3, cfg.obs_flags);
+    PointHot h = st.load_step(i);
+    const float2 a = act[i];
+    float o[point::OBS], tobs[point::OBS];
+    PointExt x, tx;
+    StepResult r = point_env_step(h, st.cold, i, a.x, a.y, cfg, o, tobs, &x, &tx);
+    st.store_step(i, h, r.done);
+    emit_obs_row<point::OBS, POINT_OBS_PRE, 3, 3>(obs + i * O, o, x, cfg.obs_flags);
+    rew[i] = r.rew;
+    done[i] = r.done ? 1 : 0;
+    trunc[i] = r.trunc ? 1 : 0;
+    if (r.done) {
+        if (term_obs) emit_obs_row<point::OBS, POINT_OBS_PRE, 3, 3>(term_obs + i * O, tobs, tx, cfg.obs_flags);
+        if (ep_ret) ep_ret[i] = r.ep_r;
+        if (ep_len) ep_len[i] = r.ep_l;
+    }
+}
+
+__device__ __forceinline__ void point_obs_row_ext(const PointState& st, const PointHot& h, int64_t i, const float (&o)[point::OBS],
+                                                  unsigned flags, float* __restrict__ obs) {
+    PointExt x;
+    point_obs_ext(h, st.cold, i, x);
+    emit_obs_row<point::OBS, POINT_OBS_PRE, 3, 3>(obs + i * obs_dim_ext(point::OBS, 3, 3, flags), o, x, flags);
+}
+
 __global__ void __launch_bounds__(STEP_THREADS)
 point_reset_kernel(PointState st, const uint8_t* __restrict__ mask, int first,
-                   float* __restrict__ obs) {
+                   float* __restrict__ obs, unsigned flags) {
     const int64_t i = (int64_t)blockIdx.x * STEP_THREADS + threadIdx.x;
     if (i >= st.n) return;
     if (mask && !mask[i]) return;
@@ -110,9 +143,20 @@ point_reset_kernel(PointState st, const uint8_t* __restrict__ mask, int first,
     if (obs) {
         float o[point::OBS];
         point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy, o);
+        if (flags) { point_obs_row_ext(st, h, i, o, flags, obs); return; }
 #pragma unroll
         for (int k = 0; k < point::OBS; ++k) obs[i * point::OBS + k] = o[k];
     }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+point_obs_ext_kernel(PointState st, float* __restrict__ obs, unsigned flags) {
+    const int64_t i = (int64_t)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    PointHot h = st.load(i);
+    float o[point::OBS];
+    point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy, o);
+    point_obs_row_ext(st, h, i, o, flags, obs);
 }
 
 __global__ void __launch_bounds__(STEP_THREADS)
@@ -212,8 +256,47 @@ car_step_kernel(CarSoA st, car::Consts K, EnvCfg cfg, const float2* __restrict__
     }
 }
 
+// optional observation keys (EnvCfg::obs_flags != 0), see point_step_ext_kernel
 __global__ void __launch_bounds__(CAR_THREADS)
-car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int first, float* __restrict__ obs) {
+car_step_ext_kernel(CarSoA st, car::Consts K, EnvCfg cfg, const float2* __restrict__ act,
+                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                    uint8_t* __restrict__ trunc, float* __restrict__ term_obs, double* __restrict__ ep_ret,
+                    int32_t* __restrict__ ep_len) {
+    MR_CAR_SCRATCH();
+    const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    const int O = obs_dim_ext(car::OBS, 13, 11, cfg.obs_flags);
+    CarHot h = st.load(i);
+    float2 a = act[i];
+    float o[car::OBS], tobs[car::OBS];
+    CarExt x, tx;
+    StepResult r = car_env_step(K, h, st.cold, i, a.x, a.y, cfg, st.contacts != 0, o, tobs, S, &x, &tx);
+    st.store(i, h);
+    emit_obs_row<car::OBS, CAR_OBS_PRE, 13, 11>(obs + i * O, o, x, cfg.obs_flags);
+    rew[i] = r.rew;
+    done[i] = r.done ? 1 : 0;
+    trunc[i] = r.trunc ? 1 : 0;
+    if (r.done) {
+        if (term_obs) emit_obs_row<car::OBS, CAR_OBS_PRE, 13, 11>(term_obs + i * O, tobs, tx, cfg.obs_flags);
+        if (ep_ret) ep_ret[i] = r.ep_r;
+        if (ep_len) ep_len[i] = r.ep_l;
+    }
+}
+
+__device__ __forceinline__ void car_obs_row(const CarHot& h, int64_t i, const float (&o)[car::OBS], unsigned flags,
+                                            float* __restrict__ obs) {
+    if (flags) {
+        CarExt x;
+        car_obs_ext(h, x);
+        emit_obs_row<car::OBS, CAR_OBS_PRE, 13, 11>(obs + i * obs_dim_ext(car::OBS, 13, 11, flags), o, x, flags);
+    } else {
+        for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+    }
+}
+
+__global__ void __launch_bounds__(CAR_THREADS)
+car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int first, float* __restrict__ obs,
+                 unsigned flags) {
     MR_CAR_SCRATCH();
     const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
     if (i >= st.n) return;
@@ -225,19 +308,19 @@ car_reset_kernel(CarSoA st, car::Consts K, const uint8_t* __restrict__ mask, int
     if (obs) {
         float o[car::OBS];
         car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o, S);
-        for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+        car_obs_row(h, i, o, flags, obs);
     }
 }
 
 __global__ void __launch_bounds__(CAR_THREADS)
-car_obs_kernel(CarSoA st, car::Consts K, float* __restrict__ obs) {
+car_obs_kernel(CarSoA st, car::Consts K, float* __restrict__ obs, unsigned flags) {
     MR_CAR_SCRATCH();
     const int64_t i = (int64_t)blockIdx.x * CAR_THREADS + threadIdx.x;
     if (i >= st.n) return;
     CarHot h = st.load(i);
     float o[car::OBS];
     car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, st.contacts != 0, o, S);
-    for (int k = 0; k < car::OBS; ++k) obs[i * car::OBS + k] = o[k];
+    car_obs_row(h, i, o, flags, obs);
 }
 
 // reference view: qpos(13) = p quat thL thR qb ; qvel(11) = v w sL sR wb ; ctrl goal elapsed ep_ret
@@ -246,6 +329,7 @@ static int car_smem_optin() {
     static OncePerDevice once;
     if (once.first()) {
         MR_CUDA(cudaFuncSetAttribute(car_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
+        MR_CUDA(cudaFuncSetAttribute(car_step_ext_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
         MR_CUDA(cudaFuncSetAttribute(car_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
         MR_CUDA(cudaFuncSetAttribute(car_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAR_SMEM));
     }
@@ -386,6 +470,7 @@ int mr_env_create(int kind, int64_t n_envs, int device, int time_limit, int term
     e->cfg.time_limit = time_limit;
     e->cfg.terminate_on_goal = terminate_on_goal ? 1 : 0;
     e->cfg.pk = point::make_k();
+    e->cfg.obs_flags = 0;
     size_t bytes = kind == MR_ENV_POINT ? PointState::slab_bytes(n_envs) : CarSoA::slab_bytes(n_envs);
     cudaError_t err = cudaMalloc(&e->slab, bytes);
     if (err != cudaSuccess) {
@@ -440,7 +525,27 @@ void mr_env_destroy(mr_env* env) {
     delete env;
 }
 
-int mr_env_obs_dim(const mr_env* env) { return env ? (env->kind == MR_ENV_POINT ? point::OBS : car::OBS) : 0; }
+int mr_env_obs_dim(const mr_env* env) {
+    if (!env) return 0;
+    return env->kind == MR_ENV_POINT ? obs_dim_ext(point::OBS, 3, 3, env->cfg.obs_flags)
+                                     : obs_dim_ext(car::OBS, 13, 11, env->cfg.obs_flags);
+}
+
+int mr_env_set_obs_flags(mr_env* env, unsigned flags) {
+    MR_REQUIRE(env, "env is NULL");
+    if (flags & ~OBS_ALL_FLAGS) {
+        set_error("unknown observation flag bits 0x%x (1 goal_dist, 2 qpos, 4 qvel, 8 ctrl)", flags & ~OBS_ALL_FLAGS);
+        return MR_ERR_UNSUPPORTED;
+    }
+    if (env->scratch && flags != env->cfg.obs_flags) {   // mr_rollout_unfused sized its scratch for the old row length
+        DeviceGuard guard(env->device);
+        MR_CUDA(cudaDeviceSynchronize());
+        MR_CUDA(cudaFree(env->scratch));
+        env->scratch = nullptr;
+    }
+    env->cfg.obs_flags = flags;
+    return MR_OK;
+}
 int mr_env_state_dim(const mr_env* env) {
     return env ? (env->kind == MR_ENV_POINT ? POINT_STATE_DIM : CAR_STATE_DIM) : 0;
 }
@@ -469,10 +574,12 @@ int mr_env_reset(mr_env* env, const uint8_t* mask, int first, float* obs_out, vo
     MR_REQUIRE(env, "env is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     if (env->kind == MR_ENV_POINT)
-        point_reset_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, mask, first, obs_out);
+        point_reset_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, mask, first, obs_out,
+                                                                                   env->cfg.obs_flags);
     else {
         if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
-        car_reset_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, mask, first, obs_out);
+        car_reset_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, mask, first, obs_out,
+                                                                                      env->cfg.obs_flags);
     }
     MR_CHECK_LAUNCH();
     return MR_OK;
@@ -482,7 +589,17 @@ int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* 
                 uint8_t* trunc, float* term_obs, double* ep_ret, int32_t* ep_len, void* stream) {
     MR_REQUIRE(env && act && obs && rew && done && trunc, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (env->kind == MR_ENV_POINT) {
+    if (env->cfg.obs_flags) {
+        const float2* a2 = reinterpret_cast<const float2*>(act);
+        if (env->kind == MR_ENV_POINT) {
+            point_step_ext_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(
+                env->point, env->cfg, a2, obs, rew, done, trunc, term_obs, ep_ret, ep_len);
+        } else {
+            if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
+            car_step_ext_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(
+                env->car, env->carK, env->cfg, a2, obs, rew, done, trunc, term_obs, ep_ret, ep_len);
+        }
+    } else if (env->kind == MR_ENV_POINT) {
         // tuning knobs (measured on B200 at 4M envs, profiles/r01_env_step_sweep.txt): 5 blocks per SM
         // (96 registers, no spills) and a prefetch distance of 4 blocks per SM are the defaults
         static const int minb = getenv("MR_STEP_MINB") ? atoi(getenv("MR_STEP_MINB")) : 5;
@@ -509,11 +626,15 @@ int mr_env_step(mr_env* env, const float* act, float* obs, float* rew, uint8_t* 
 int mr_env_get_obs(mr_env* env, float* obs_out, void* stream) {
     MR_REQUIRE(env && obs_out, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (env->kind == MR_ENV_POINT)
-        point_obs_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, obs_out);
-    else {
+    if (env->kind == MR_ENV_POINT) {
+        if (env->cfg.obs_flags)
+            point_obs_ext_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, obs_out, env->cfg.obs_flags);
+        else
+            point_obs_kernel<<<ceil_div(env->n, STEP_THREADS), STEP_THREADS, 0, s>>>(env->point, obs_out);
+    } else {
         if (car_smem_optin() != MR_OK) return MR_ERR_CUDA;
-        car_obs_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, obs_out);
+        car_obs_kernel<<<ceil_div(env->n, CAR_THREADS), CAR_THREADS, CAR_SMEM, s>>>(env->car, env->carK, obs_out,
+                                                                                    env->cfg.obs_flags);
     }
     MR_CHECK_LAUNCH();
     return MR_OK;

@@ -104,9 +104,27 @@ __device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool
     cold.counts[2 * i] += 1;
 }
 
+using CarExt = ObsExt<13, 11>;
+constexpr int CAR_OBS_PRE = 15;
+
+// data.qpos = free joint (pos, quat) + wheel angles + rear ball quat; data.qvel = free joint (linear world, angular
+// body) + wheel rates + ball angular velocity: the order of mr_env_get_state's reference view.
+__device__ inline void car_obs_ext(const CarHot& h, CarExt& x) {
+    const car::State& s = h.s;
+    x.ctrl[0] = h.cx; x.ctrl[1] = h.cz;
+    x.goal_dist = (float)exp(-point::dist2((double)h.gx, (double)h.gy, s.p[0], s.p[1]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x.qpos[k] = (float)s.p[k]; x.qvel[k] = (float)s.v[k]; x.qvel[3 + k] = (float)s.w[k]; x.qvel[8 + k] = (float)s.wb[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x.qpos[3 + k] = (float)s.q[k]; x.qpos[9 + k] = (float)s.qb[k]; }
+    x.qpos[7] = (float)s.th[0]; x.qpos[8] = (float)s.th[1];
+    x.qvel[6] = (float)s.s[0]; x.qvel[7] = (float)s.s[1];
+}
+
 __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const EnvCold& cold, int64_t i,
                                           float a0, float a1, const EnvCfg& cfg, bool contacts, float* obs,
-                                          float* term_obs, const car::Scratch& S) {
+                                          float* term_obs, const car::Scratch& S, CarExt* ext = nullptr,
+                                          CarExt* term_ext = nullptr) {
     StepResult r;
     h.cx = fminf(fmaxf(a0, -1.f), 1.f);
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
@@ -129,10 +147,13 @@ __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
     car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs, S);
+    if (ext) car_obs_ext(h, *ext);
     if (r.done) {
         for (int k = 0; k < car::OBS; ++k) term_obs[k] = obs[k];
+        if (ext) *term_ext = *ext;
         car_reset(h, cold, i, !r.reach);
         car::sensors(K, h.s, (double)h.cx, (double)h.cz, h.gx, h.gy, contacts, obs, S);
+        if (ext) car_obs_ext(h, *ext);
     }
     return r;
 }

@@ -14,7 +14,50 @@ struct EnvCfg {
     int time_limit;         // <= 0: no TimeLimit wrapper
     int terminate_on_goal;  // EnvWrapper(terminate_on_goal=...)
     point::K pk;            // integrator constants of the point robot (constant-bank operands)
+    unsigned obs_flags;     // optional Engine.obs() keys (OBS_*); 0 = the configuration wrapper.py:293-317 builds
 };
+
+// Optional observation keys of Engine.obs() (flags src/mobrob/envs/mujoco_robots/robots/engine.py:125,140-142,
+// values engine.py:1179-1180 and 1243-1248): goal_dist = exp(-|goal - pos|_xy), qpos / qvel = data.qpos / data.qvel,
+// ctrl = data.ctrl (the clipped action of the last step).  The flat row is the concatenation in SORTED key order
+// (engine.py:1253-1259), so the extra keys are interleaved with the sensors:
+//   accelerometer [ballangvel_rear ballquat_rear] | ctrl | goal_compass | goal_dist | gyro magnetometer | qpos | qvel | velocimeter
+constexpr unsigned OBS_GOAL_DIST = 1u, OBS_QPOS = 2u, OBS_QVEL = 4u, OBS_CTRL = 8u, OBS_ALL_FLAGS = 15u;
+
+template <int NQ, int NV>
+struct ObsExt {
+    float ctrl[2];
+    float goal_dist;
+    float qpos[NQ];
+    float qvel[NV];
+};
+
+__host__ __device__ inline int obs_dim_ext(int base, int nq, int nv, unsigned f) {
+    return base + ((f & OBS_CTRL) ? 2 : 0) + ((f & OBS_GOAL_DIST) ? 1 : 0) + ((f & OBS_QPOS) ? nq : 0) + ((f & OBS_QVEL) ? nv : 0);
+}
+
+// BASE floats of the default row, PRE of them in front of goal_compass (= in front of "ctrl")
+template <int BASE, int PRE, int NQ, int NV>
+__device__ __forceinline__ void emit_obs_row(float* __restrict__ dst, const float* base, const ObsExt<NQ, NV>& x, unsigned f) {
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < PRE; ++j) dst[k++] = base[j];
+    if (f & OBS_CTRL) { dst[k++] = x.ctrl[0]; dst[k++] = x.ctrl[1]; }
+    dst[k++] = base[PRE]; dst[k++] = base[PRE + 1];
+    if (f & OBS_GOAL_DIST) dst[k++] = x.goal_dist;
+#pragma unroll
+    for (int j = PRE + 2; j < BASE - 3; ++j) dst[k++] = base[j];
+    if (f & OBS_QPOS) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) dst[k++] = x.qpos[j];
+    }
+    if (f & OBS_QVEL) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dst[k++] = x.qvel[j];
+    }
+#pragma unroll
+    for (int j = BASE - 3; j < BASE; ++j) dst[k++] = base[j];
+}
 
 // Arrays touched only by resets (and by the reference-view export).
 struct EnvCold {
@@ -87,11 +130,33 @@ __device__ inline void point_reset(PointHot& h, const EnvCold& cold, int64_t i, 
     cold.counts[2 * i] += 1;
 }
 
+using PointExt = ObsExt<3, 3>;
+constexpr int POINT_OBS_PRE = 3;
+
+// qpos / qvel are the joint coordinates (two slides in the robot body's frame, one hinge), relative to the body
+// pose PointEnv.set_pos wrote into the model (wrapper.py:301-305): the same view mr_env_get_state exports.
+__device__ inline void point_obs_ext(const PointHot& h, const EnvCold& cold, int64_t i, PointExt& x) {
+    x.ctrl[0] = h.cx; x.ctrl[1] = h.cz;
+    x.goal_dist = (float)exp(-point::dist2((double)h.gx, (double)h.gy, h.d.px, h.d.py));
+    const float2 b = cold.body_xy[i];
+    const double p0 = cold.psi0[i];
+    double s0, c0;
+    sincos(p0, &s0, &c0);
+    const double dx = h.d.px - (double)b.x, dy = h.d.py - (double)b.y;
+    x.qpos[0] = (float)(c0 * dx + s0 * dy);
+    x.qpos[1] = (float)(-s0 * dx + c0 * dy);
+    x.qpos[2] = (float)(h.d.psi - p0);
+    x.qvel[0] = (float)(c0 * h.d.vx + s0 * h.d.vy);
+    x.qvel[1] = (float)(-s0 * h.d.vx + c0 * h.d.vy);
+    x.qvel[2] = (float)h.d.om;
+}
+
 // One VecEnv step of one env.  obs receives the row the VecEnv returns (post-reset when
-// done); term_obs receives info["terminal_observation"] when done.
+// done); term_obs receives info["terminal_observation"] when done.  ext / term_ext (may be NULL): the optional keys
+// of the same two observations.
 __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, int64_t i,
                                             float a0, float a1, const EnvCfg& cfg, float* obs,
-                                            float* term_obs) {
+                                            float* term_obs, PointExt* ext = nullptr, PointExt* term_ext = nullptr) {
     StepResult r;
     h.cx = fminf(fmaxf(a0, -1.f), 1.f);  // engine.py:1401-1405
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
@@ -114,11 +179,14 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;
     point::sensors_cs(cfg.pk, h.d, hc, hs, (double)h.cx, (double)h.cz, h.gx, h.gy, obs, dcur);
+    if (ext) point_obs_ext(h, cold, i, *ext);
     if (r.done) {
 #pragma unroll
         for (int k = 0; k < point::OBS; ++k) term_obs[k] = obs[k];
+        if (ext) *term_ext = *ext;
         point_reset(h, cold, i, !r.reach);
         point::sensors(h.d, (double)h.cx, (double)h.cz, h.gx, h.gy, obs);
+        if (ext) point_obs_ext(h, cold, i, *ext);
     }
     return r;
 }

@@ -223,6 +223,7 @@ extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* la
                    logp && last_val && last_done && ep_r && ep_l && ep_count,
                "NULL argument");
     MR_REQUIRE(env->kind == MR_ENV_POINT, "fused rollout is built for the point env");
+    MR_REQUIRE(env->cfg.obs_flags == 0, "fused rollout is built for the default observation (use mr_rollout_unfused)");
     MR_REQUIRE(T > 0 && ring_cap > 0, "T and ring_cap must be positive");
     RolloutArgs A;
     A.st = env->point;

@@ -126,10 +126,17 @@ class MujocoGoalEnv(EnvWrapper, ABC):
     ENV_NAME = ""
     placements_extents = (-2, -2, 2, 2)  # engine.py:101
 
+    def get_robot_config(self) -> dict:
+        """Engine config of the robot (wrapper.py:235-240, 293-317).  A subclass may switch on observe_goal_dist /
+        observe_qpos / observe_qvel / observe_ctrl (engine.py:125, 140-142); other observation keys are fixed."""
+        return {"robot_base": f"xmls/{self.ENV_NAME}.xml", "sensors_obs": self.BASE_SENSORS,
+                "observe_com": False, "observe_goal_comp": True}
+
     def build_env(self):
         # time limit / termination are handled by this class (the GPU env runs raw steps)
         self._engine_seed = 0
-        return GpuVecEnv(self.ENV_NAME, 1, seed=None, time_limit=None, terminate_on_goal=False)
+        return GpuVecEnv(self.ENV_NAME, 1, seed=None, time_limit=None, terminate_on_goal=False,
+                         robot_config=self.get_robot_config())
 
     def get_observation_space(self):
         return self.env.observation_space

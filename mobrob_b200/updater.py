@@ -16,6 +16,9 @@ class PpoUpdater:
                  eps: float = 1e-5, max_grad_norm: float = 0.5, clip_range: float = 0.2,
                  ent_coef: float = 0.0, vf_coef: float = 0.5, normalize_advantage: bool = True):
         self.lib = _lib.load()
+        if not 0 < obs_dim < 32:
+            raise ValueError(f"the PPO kernels take observations of 1..31 floats (got {obs_dim}): with the optional "
+                             "observation keys, the car's qpos / qvel do not fit")
         self.obs_dim = obs_dim
         self.device = device
         self.lr, self.betas, self.eps = lr, betas, eps

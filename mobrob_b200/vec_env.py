@@ -18,12 +18,33 @@ from .spaces import Box
 
 ENV_KINDS = {"point": 0, "car": 1}
 OBS_DIMS = {"point": 14, "car": 26}
+# Engine config keys (engine.py:124-144) the batched env implements -> mr_env_set_obs_flags bits; every other
+# observe_* key must keep the value the reference's get_robot_config leaves it at
+OBS_FLAG_BITS = {"observe_goal_dist": 1, "observe_qpos": 2, "observe_qvel": 4, "observe_ctrl": 8}
+_FIXED_OBSERVE = {"observe_sensors": True, "observe_goal_comp": True, "observe_com": False, "observe_goal_lidar": False,
+                  "observe_box_comp": False, "observe_box_lidar": False, "observe_circle": False,
+                  "observe_remaining": False, "observe_walls": False, "observe_hazards": False, "observe_vases": False,
+                  "observe_pillars": False, "observe_buttons": False, "observe_gremlins": False,
+                  "observe_vision": False, "observe_freejoint": False}
+
+
+def obs_flags_of(robot_config: dict | None) -> int:
+    """Engine(config) observation switches -> flag bits.  Keys that do not concern the observation (robot_base,
+    sensors_obs, box_*) are the reference's constants for the robot and are ignored."""
+    flags = 0
+    for key, value in (robot_config or {}).items():
+        if key in OBS_FLAG_BITS:
+            flags |= OBS_FLAG_BITS[key] if value else 0
+        elif key in _FIXED_OBSERVE and bool(value) != _FIXED_OBSERVE[key]:
+            raise NotImplementedError(f"{key}={value!r}: only {sorted(OBS_FLAG_BITS)} can be switched on the B200 path")
+    return flags
 
 
 class GpuVecEnv:
     def __init__(self, env_name: str = "point", n_envs: int = 1, seed: int | None = 0,
                  time_limit: int | None = 1000, terminate_on_goal: bool = True,
-                 device: int | torch.device | None = None, first_rank: int = 0):
+                 device: int | torch.device | None = None, first_rank: int = 0,
+                 robot_config: dict | None = None):
         if env_name not in ENV_KINDS:
             raise ValueError(f"Env {env_name} not found")  # wrapper.py:566
         if not torch.cuda.is_available():
@@ -42,6 +63,9 @@ class GpuVecEnv:
                                           int(time_limit or 0), int(self.terminate_on_goal),
                                           ctypes.byref(h)))
         self._h = h
+        self.obs_flags = obs_flags_of(robot_config)
+        if self.obs_flags:
+            _lib.check(self.lib.mr_env_set_obs_flags(h, self.obs_flags))
         self.obs_dim = int(self.lib.mr_env_obs_dim(h))
         self.state_dim = int(self.lib.mr_env_state_dim(h))
         self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,), np.float32)

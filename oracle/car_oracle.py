@@ -357,6 +357,15 @@ class CarBody:
         o[:, 23:26] = mtv(R, self.v)
         return o.astype(np.float32)
 
+    # -- optional Engine.obs() keys (engine.py:1243-1248), MuJoCo order: free joint, wheel hinges, rear ball ----------
+    obs_pre = 15  # floats of the default row in front of goal_compass (accelerometer, ballangvel_rear, ballquat_rear)
+
+    def qpos(self):
+        return np.concatenate([self.p, self.quat, self.th, self.qb], 1)
+
+    def qvel(self):
+        return np.concatenate([self.v, self.w, self.s, self.wb], 1)
+
     def state_vector(self):
         """qpos(13) qvel(11) ctrl(2), MuJoCo order."""
         return np.concatenate([self.p, self.quat, self.th, self.qb, self.v, self.w, self.s, self.wb, self.ctrl], 1)

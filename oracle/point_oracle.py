@@ -162,6 +162,15 @@ class PointBody:
         o[:, 12] = -st * vx + ct * vy
         return o.astype(np.float32)
 
+    # -- optional Engine.obs() keys (engine.py:1243-1248): data.qpos / data.qvel are the joint coordinates ----------
+    obs_pre = 3  # floats of the default row in front of goal_compass (accelerometer)
+
+    def qpos(self):
+        return self.q.copy()
+
+    def qvel(self):
+        return self.v.copy()
+
     # -- state export (tests) -----------------------------------------------------
     def state_vector(self):
         return np.concatenate(

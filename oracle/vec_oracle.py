@@ -27,10 +27,38 @@ def dist2(ax, ay, bx, by):
     return np.sqrt(dx * dx + dy * dy)
 
 
+def extend_obs(body, base, goal, observe):
+    """Engine.obs() with the optional keys (src/mobrob/envs/mujoco_robots/robots/engine.py:1179-1180 goal_dist =
+    exp(-dist_goal()), engine.py:1243-1248 qpos / qvel / ctrl), flattened in sorted key order (engine.py:1253-1259):
+    accelerometer [ballangvel_rear ballquat_rear] ctrl goal_compass goal_dist gyro magnetometer qpos qvel velocimeter.
+    ``base`` is the default row (body.obs); ``observe`` the config dict (observe_goal_dist / qpos / qvel / ctrl).
+    Parity unpinned beyond the restated source: no shipped artefact was produced with these keys switched on."""
+    observe = observe or {}
+    if not any(observe.get(k) for k in ("observe_goal_dist", "observe_qpos", "observe_qvel", "observe_ctrl")):
+        return base
+    pre, n_base = body.obs_pre, base.shape[1]
+    parts = [base[:, :pre]]
+    if observe.get("observe_ctrl"):
+        parts.append(body.ctrl)
+    parts.append(base[:, pre:pre + 2])
+    if observe.get("observe_goal_dist"):
+        p = body.pos()
+        g = np.asarray(goal, dtype=np.float64)
+        parts.append(np.exp(-dist2(g[:, 0], g[:, 1], p[:, 0], p[:, 1]))[:, None])
+    parts.append(base[:, pre + 2:n_base - 3])
+    if observe.get("observe_qpos"):
+        parts.append(body.qpos())
+    if observe.get("observe_qvel"):
+        parts.append(body.qvel())
+    parts.append(base[:, n_base - 3:])
+    return np.concatenate([np.asarray(x, dtype=np.float64) for x in parts], axis=1).astype(np.float32)
+
+
 class GoalVecOracle:
     def __init__(self, body, seed: int = 0, time_limit: int | None = 1000,
-                 terminate_on_goal: bool = True):
+                 terminate_on_goal: bool = True, observe: dict | None = None):
         self.body = body
+        self.observe = observe
         self.n = body.n
         self.seed0 = seed
         self.time_limit = time_limit
@@ -95,7 +123,10 @@ class GoalVecOracle:
             self._reset_env(i, seed=self.seed0 + i)
         self.first_reset = False
         self.prev_pos = self.body.pos()
-        return self.body.obs(self.goal)
+        return self._obs()
+
+    def _obs(self):
+        return extend_obs(self.body, self.body.obs(self.goal), self.goal, self.observe)
 
     # ------------------------------------------------------------------------
     def step(self, actions):
@@ -122,7 +153,7 @@ class GoalVecOracle:
             truncated = np.zeros(self.n, dtype=bool)
         done = terminated | truncated
         self.ep_ret += reward
-        obs = b.obs(self.goal)
+        obs = self._obs()
         infos = {
             "terminal_obs": obs.copy(),
             "truncated": truncated & ~terminated,
@@ -135,6 +166,6 @@ class GoalVecOracle:
             for i in np.nonzero(done)[0]:
                 self._reset_env(int(i), reached_i=bool(reach[i]))
             self.prev_pos = b.pos()
-            new_obs = b.obs(self.goal)
+            new_obs = self._obs()
             obs = np.where(done[:, None], new_obs, obs)
         return obs, reward.astype(np.float32), done, infos
