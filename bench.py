@@ -298,20 +298,21 @@ def run_ours(args):
     ev[2].record()
     barrier()
     rollout_ms, train_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    epoch_ms = time_epoch_kernel(model, dev, batch)
+    launch_ms, launch_epochs = time_update_kernel(model, dev, batch)
     peaks, peaks_src = measured_peaks()
     fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     tensor_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone
     flops = FLOPS[env_name]
-    achieved = flops * steps_per_iter / (epoch_ms * 1e-3) / 1e12
+    achieved = flops * steps_per_iter * launch_epochs / (launch_ms * 1e-3) / 1e12
     default_cfg = (env_name, n_envs, n_steps, batch) == ("point", N_ENVS, N_STEPS, BATCH)
     kp = 16 if OBS_DIM[env_name] + 1 <= 16 else 32
-    roofline = {"kernel": f"ppo_epoch_tc_kernel<{kp}> (one launch = one epoch = {steps_per_iter // batch} minibatch updates: "
+    roofline = {"kernel": f"ppo_epoch_tc_kernel<{kp}> (one launch = {launch_epochs} epoch(s) = "
+                          f"{launch_epochs * (steps_per_iter // batch)} minibatch updates: "
                           "tcgen05 forward/backward GEMMs, bulk-reduced gradient, clip, Adam)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES if default_cfg else None,
-                "ms_per_launch": epoch_ms,
-                "algorithmic": f"{flops} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples per launch",
+                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES * launch_epochs if default_cfg else None,
+                "ms_per_launch": launch_ms, "epochs_per_launch": launch_epochs,
+                "algorithmic": f"{flops} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples x {launch_epochs} epoch(s) per launch",
                 "peak_source": f"bf16_tflops of MEASURED_PEAKS.json ({peaks_src})",
                 "tensor_flops_issued_per_algorithmic_flop": 3,
                 "frac_issued": 3 * achieved / tensor_peak,
@@ -321,7 +322,7 @@ def run_ours(args):
                         "per-minibatch dependency chain (element-wise passes between the GEMMs, one grid barrier), see profiles/",
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/ (per launch)",
                 "step_share": {"rollout_ms": rollout_ms, "update_ms": train_ms,
-                               "epoch_kernel_ms_x_epochs": epoch_ms * N_EPOCHS}}
+                               "update_kernel_ms": launch_ms * (N_EPOCHS // launch_epochs)}}
     env_roof = None
     if default_cfg and not args.no_extras and world == 1:
         env_roof = time_env_step_kernel(dev, peaks)
@@ -426,30 +427,33 @@ EPOCH_KERNEL_DRAM_BYTES = 158.05e6  # 154.2 MB read + 3.9 MB written (profiles/r
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
-def time_epoch_kernel(model, dev, batch=BATCH):
-    """Average duration of the epoch kernel alone, CUDA events on the launching stream.  Parameters
-    and Adam state are restored afterwards (the launches are real updates)."""
+def time_update_kernel(model, dev, batch=BATCH):
+    """Average duration of the update's cooperative launch alone, shaped as PPO.train launches it (every epoch of
+    the update in ONE launch when the rollout divides into whole minibatches, else one epoch), CUDA events on the
+    launching stream.  Returns (ms per launch, epochs per launch).  Parameters and Adam state are restored
+    afterwards (the launches are real updates)."""
     import torch
 
     up, b = model.updater, model.buf
     T, N = model.n_steps, model.env.num_envs
     saved = [t.clone() for t in (up.params, up.exp_avg, up.exp_avg_sq, up.step)]
-    perm = torch.randperm(T * N, device=dev, dtype=torch.int64)
-    stats = up.adv_stats(b["advantages"], perm, batch, N, T)
+    epochs = model.n_epochs if (T * N) % batch == 0 and model.n_epochs <= 32 else 1
+    stats, rows = up.prepare_epochs_device(b["advantages"], 12345, list(range(epochs)), batch, N, T)
+    stats, rows = stats.view(-1, 3), rows[:epochs].reshape(-1)
     up.pack(b)
     for _ in range(2):
-        up.train_epoch_fused(None, perm, stats, batch, N, T)
+        up.train_epoch_fused(None, None, stats, batch, N, T, rows=rows)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 3
     e0.record()
     for _ in range(reps):
-        up.train_epoch_fused(None, perm, stats, batch, N, T)
+        up.train_epoch_fused(None, None, stats, batch, N, T, rows=rows)
     e1.record()
     torch.cuda.synchronize(dev)
     for t, sv in zip((up.params, up.exp_avg, up.exp_avg_sq, up.step), saved):
         t.copy_(sv)
-    return e0.elapsed_time(e1) / reps
+    return e0.elapsed_time(e1) / reps, epochs
 
 
 def time_env_step_kernel(dev, peaks):

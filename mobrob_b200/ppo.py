@@ -365,9 +365,16 @@ class PPO:
             if d is not None:
                 flat, _ = sharding.allreduce_adv_stats(stats_all.view(-1, 3))
                 stats_all = flat.view(self.n_epochs, n_mb, 3)
-            for epoch in range(self.n_epochs):
-                up.train_epoch_fused(None, None, stats_all[epoch], B, N, T, log[k:k + n_mb], self._xchg, rows=rows_all[epoch])
-                k += n_mb
+            if n % B == 0 and not os.environ.get("MR_EPOCH_LAUNCHES"):
+                # whole minibatches only: the epochs are one sequence of n_epochs * n_mb minibatches over the concatenated
+                # row lists -- ONE cooperative launch for the update (the tower state is staged into shared memory and
+                # written back once instead of once per epoch)
+                up.train_epoch_fused(None, None, stats_all.view(-1, 3), B, N, T, log[:rows], self._xchg, rows=rows_all.view(-1))
+                k = rows
+            else:
+                for epoch in range(self.n_epochs):
+                    up.train_epoch_fused(None, None, stats_all[epoch], B, N, T, log[k:k + n_mb], self._xchg, rows=rows_all[epoch])
+                    k += n_mb
             epochs = ()
         else:
             epochs = range(self.n_epochs)

@@ -23,5 +23,5 @@ for _ in range(2):
     model.collect_rollouts()
     model.train()
 torch.cuda.synchronize()
-ms = [bench.time_epoch_kernel(model, dev) for _ in range(3)]
+ms = [bench.time_update_kernel(model, dev)[0] / model.n_epochs for _ in range(3)]
 print(f"AB_EPOCH env={env_name} kernel={os.environ.get('MR_PPO_EPOCH', 'v2')} ms_per_epoch={min(ms):.4f} all={ms}")
