@@ -310,7 +310,7 @@ def run_ours(args):
                           f"{launch_epochs * (steps_per_iter // batch)} minibatch updates: "
                           "tcgen05 forward/backward GEMMs, bulk-reduced gradient, clip, Adam)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": EPOCH_KERNEL_DRAM_BYTES * launch_epochs if default_cfg else None,
+                "frac": achieved / tensor_peak, "traffic": UPDATE_KERNEL_DRAM_BYTES.get(launch_epochs) if default_cfg else None,
                 "ms_per_launch": launch_ms, "epochs_per_launch": launch_epochs,
                 "algorithmic": f"{flops} FLOP/sample/epoch (SURVEY 8d) x {steps_per_iter} samples x {launch_epochs} epoch(s) per launch",
                 "peak_source": f"bf16_tflops of MEASURED_PEAKS.json ({peaks_src})",
@@ -422,8 +422,10 @@ def run_ours(args):
 EP_D2H_BYTES = 100 * 12 + 8
 
 
-# dram bytes of one ppo_epoch_tc_kernel launch (ncu --set full, see profiles/README.md)
-EPOCH_KERNEL_DRAM_BYTES = 158.05e6  # 154.2 MB read + 3.9 MB written (profiles/r02_ncu_full.txt)
+# dram bytes of one ppo_epoch_tc_kernel launch of the default workload by epochs per launch (ncu --set full,
+# profiles/r02_ncu_full.txt): 10 epochs 1157.5 MB read + 4.7 MB written (the 116 MB of records partly stay in the
+# 126 MB L2 from one epoch to the next); a single-epoch launch 154.2 MB + 3.9 MB
+UPDATE_KERNEL_DRAM_BYTES = {10: 1162.2e6, 1: 158.05e6}
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
