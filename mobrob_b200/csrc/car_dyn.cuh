@@ -39,6 +39,7 @@ constexpr double MAG_Y = -0.5;
 constexpr double GOAL_Z = 0.3 / 2 + 1e-2;  // engine.py:794
 constexpr double R_WHEEL = 0.05, HALF_LEN = 0.025, R_CASTER = 0.05;
 constexpr int N_SWEEPS = 10;
+constexpr int N_SWEEPS_WARM = 4;
 constexpr double MU = 1.0;
 constexpr double TC = 0.02, DR = 1.0, IMP_D0 = 0.9, IMP_DMAX = 0.95, IMP_WIDTH = 0.001;
 constexpr int OBS = 26;
@@ -244,11 +245,12 @@ struct Scratch {
 constexpr int N_ROWS = 15;                              // 5 contacts x (world x, world y, normal)
 constexpr int A_ENTRIES = N_ROWS * (N_ROWS + 1) / 2;    // packed upper triangle
 constexpr int SCR_RES = A_ENTRIES;                      // resid0[15]
-constexpr int SCR_REG = SCR_RES + N_ROWS;               // Rreg[15]
-constexpr int SCR_INV = SCR_REG + N_ROWS;               // 1 / (A_ii + Rreg_i)
-constexpr int SCR_TW = SCR_INV + N_ROWS;                // Tw[5][9]
-constexpr int SCR_PW = SCR_TW + 45;                     // p[5][3]
-constexpr int SCRATCH_DOUBLES = SCR_PW + 15;            // 225 doubles = 1800 B per thread
+constexpr int SCR_INV = SCR_RES + N_ROWS;               // 1 / (A_ii + Rreg_i), Rreg_i = (1 - imp_c) / imp_c * A_ii
+constexpr int SCR_IMP = SCR_INV + N_ROWS;               // imp_c[5] = A_ii / (A_ii + Rreg_i)
+constexpr int SCR_TW = SCR_IMP + 5;                     // Tw[5][9]
+constexpr int SCR_PW = SCR_TW + 45;                     // p of contacts 0 and 2 (the first rim point of each wheel)
+constexpr int SCR_FL = SCR_PW + 6;                      // the forces of the last solve: the next substep's starting point
+constexpr int SCRATCH_DOUBLES = SCR_FL + N_ROWS;        // 221 doubles = 1768 B per thread (2 x 64 threads per SM: <= 1816)
 __host__ __device__ constexpr int a_index(int i, int j) {   // i <= j
     return i * N_ROWS - i * (i - 1) / 2 + (j - i);
 }
@@ -306,7 +308,7 @@ __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, c
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         pj[k] = F.R[3 * k + 1] * (-ct.rB[2]) + F.R[3 * k + 2] * ct.rB[1];
-        S.st(SCR_PW + 3 * cj + k, pj[k]);
+        if (cj == 0 || cj == 2) S.st(SCR_PW + 3 * (cj >> 1) + k, pj[k]);   // read by the wheel's second rim point
     }
 #pragma unroll
     for (int ci = 0; ci <= cj; ++ci) {
@@ -321,7 +323,7 @@ __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, c
                 const double t2 = ci == cj ? Twj[6 + k] : S.ld(SCR_TW + 9 * ci + 6 + k);
                 double v = t0 * Vwj[l] + t1 * Vwj[3 + l] + t2 * Vwj[6 + l];
                 if (k == l) v += im;
-                if (same_wheel) v += (ci == cj ? pj[k] : S.ld(SCR_PW + 3 * ci + k)) * pj[l] * iax;
+                if (same_wheel) v += (ci == cj ? pj[k] : S.ld(SCR_PW + 3 * (ci >> 1) + k)) * pj[l] * iax;
                 S.st(a_index(3 * ci + k, 3 * cj + l), v);
             }
     }
@@ -355,20 +357,23 @@ __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, c
         const double Aii = S.ld(a_index(i, i));
         const double Rreg = (1.0 - ct.imp) / ct.imp * Aii;
         S.st(SCR_RES + i, dot3(aa, d) - aref);
-        S.st(SCR_REG + i, Rreg);
         S.st(SCR_INV + i, 1.0 / (Aii + Rreg));
     }
+    S.st(SCR_IMP + cj, ct.imp);
 }
 
 // Projected Gauss-Seidel on the Delassus matrix; fl[3 c + k]: k = 0, 1 world-x / world-y tangents, 2 normal.
-// Returns the mask of active contacts (0: fl is all zero).
+// Cold: N_SWEEPS sweeps from zero forces.  warm (substeps 2..10 of an env step): N_SWEEPS_WARM sweeps from the
+// forces the previous substep's solve left in the scratch (zero for contacts that are not active now) -- the contact
+// set persists from one 4 ms substep to the next, and 10 + 9 x 4 sweeps per env step end as close to the
+// converged forces as 10 x 10 cold ones did (tools/experiments/car_warm_start_probe.py).  Every solve leaves its
+// forces in the scratch.  Returns the mask of active contacts (0: fl is all zero).
 __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const Frame& F, bool contacts, double (&fl)[N_ROWS],
-                                          const Scratch& S) {
+                                          const Scratch& S, bool warm) {
 #pragma unroll
     for (int i = 0; i < N_ROWS; ++i) fl[i] = 0.0;
-    if (!contacts) return 0u;
     unsigned active = 0u;
-    {
+    if (contacts) {
         const double zB[3] = {F.R[6], F.R[7], F.R[8]};
         active |= contact_geometry<0>(K, zB, s.p[2]).active ? 1u : 0u;
         active |= contact_geometry<1>(K, zB, s.p[2]).active ? 2u : 0u;
@@ -376,7 +381,11 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
         active |= contact_geometry<3>(K, zB, s.p[2]).active ? 8u : 0u;
         active |= contact_geometry<4>(K, zB, s.p[2]).active ? 16u : 0u;
     }
-    if (!active) return 0u;
+    if (!active) {
+#pragma unroll
+        for (int i = 0; i < N_ROWS; ++i) S.st(SCR_FL + i, 0.0);
+        return 0u;
+    }
     {
         Gen a_free, vel;
         solve<false, true>(K, F.smooth, F.B, a_free);
@@ -394,17 +403,34 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
     double r[N_ROWS];
 #pragma unroll
     for (int i = 0; i < N_ROWS; ++i) r[i] = S.ld(SCR_RES + i);
-#pragma unroll 1
-    for (int sweep = 0; sweep < N_SWEEPS; ++sweep) {
+    if (warm) {
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             if (!(active >> c & 1u)) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = 3 * c + k;
+                const double f = S.ld(SCR_FL + i);
+                fl[i] = f;
+#pragma unroll
+                for (int j = 0; j < N_ROWS; ++j) r[j] += a_get(S, i, j) * f;
+            }
+        }
+    }
+    const int n_sweeps = warm ? N_SWEEPS_WARM : N_SWEEPS;
+#pragma unroll 1
+    for (int sweep = 0; sweep < n_sweeps; ++sweep) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            if (!(active >> c & 1u)) continue;
+            const double imp = S.ld(SCR_IMP + c);
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk) {
                 const int k = kk == 0 ? 2 : kk - 1;
                 const int i = 3 * c + k;
                 const double cur = fl[i];
-                double nw = cur - (r[i] + S.ld(SCR_REG + i) * cur) * S.ld(SCR_INV + i);
+                // cur - (r_i + Rreg_i cur) / (A_ii + Rreg_i), with Rreg_i / (A_ii + Rreg_i) = 1 - imp_c
+                double nw = imp * cur - r[i] * S.ld(SCR_INV + i);
                 if (k == 2) nw = fmax(nw, 0.0);
                 else { const double lim = MU * fl[3 * c + 2]; nw = fmin(fmax(nw, -lim), lim); }
                 const double delta = nw - cur;
@@ -414,6 +440,8 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < N_ROWS; ++i) S.st(SCR_FL + i, fl[i]);
     return active;
 }
 
@@ -446,11 +474,12 @@ __device__ inline void add_contact_loads(const Consts& K, const State& s, const 
     if (active & 16u) add_contact_load<4>(K, s, F, fl, L);
 }
 
-__device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts, const Scratch& S) {
+// warm: this is not the first substep of the env step (the scratch holds the previous substep's contact forces)
+__device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts, const Scratch& S, bool warm) {
     Frame F;
     make_frame(K, s, c0, c1, F);
     double fl[N_ROWS];
-    const unsigned active = solve_contacts(K, s, F, contacts, fl, S);
+    const unsigned active = solve_contacts(K, s, F, contacts, fl, S, warm);
     Loads L;
     add_contact_loads(K, s, F, active, fl, L);
     Gen acc;
@@ -476,7 +505,7 @@ __device__ inline void sensors(const Consts& K, const State& s, double c0, doubl
     Frame F;
     make_frame(K, s, c0, c1, F);
     double fl[N_ROWS];
-    const unsigned active = solve_contacts(K, s, F, contacts, fl, S);
+    const unsigned active = solve_contacts(K, s, F, contacts, fl, S, false);   // a function of the state alone: always cold
     Loads L;
     add_contact_loads(K, s, F, active, fl, L);
     Gen acc;

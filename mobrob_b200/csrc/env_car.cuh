@@ -130,7 +130,7 @@ __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const
     h.cz = fminf(fmaxf(a1, -1.f), 1.f);
     const double prevx = h.s.p[0], prevy = h.s.p[1];
 #pragma unroll 1
-    for (int k = 0; k < car::FRAME_SKIP; ++k) car::substep(K, h.s, (double)h.cx, (double)h.cz, contacts, S);
+    for (int k = 0; k < car::FRAME_SKIP; ++k) car::substep(K, h.s, (double)h.cx, (double)h.cz, contacts, S, k > 0);
     const double gx = (double)h.gx, gy = (double)h.gy;
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.s.p[0], h.s.p[1]);

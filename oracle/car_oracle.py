@@ -19,7 +19,9 @@ Contacts are an APPROXIMATION of MuJoCo's soft-constraint model (parity unpinned
 five points (two rim points per wheel, one under the caster), per point one normal row and two
 tangential rows with MuJoCo's reference acceleration (solref 0.02/1, solimp 0.9/0.95/0.001) and
 regulariser R = (1 - d)/d * A_ii, solved by projected Gauss-Seidel (box friction |f_t| <= mu f_n,
-N_SWEEPS sweeps, matrix free) instead of MuJoCo's pyramidal-cone Newton solver; torsional and
+matrix free: N_SWEEPS sweeps from zero in the first substep of an env step and in obs(), N_SWEEPS_WARM
+sweeps from the previous substep's forces in the other nine -- MuJoCo warm-starts its solver from the
+previous qacc in the same spirit) instead of MuJoCo's pyramidal-cone Newton solver; torsional and
 rolling friction are dropped.
 """
 from __future__ import annotations
@@ -39,7 +41,8 @@ GOAL_Z = 0.3 / 2 + 1e-2  # engine.py:794
 R_WHEEL = 0.05
 HALF_LEN = 0.025
 R_CASTER = 0.05
-N_SWEEPS = 10
+N_SWEEPS = 10  # cold solve: first substep of an env step, and every obs()
+N_SWEEPS_WARM = 4  # substeps 2..10 of an env step start from the previous substep's forces
 MU = 1.0  # geom friction[0] default
 SOLREF_TC, SOLREF_DR = 0.02, 1.0
 IMP_D0, IMP_DMAX, IMP_WIDTH = 0.9, 0.95, 0.001
@@ -242,9 +245,10 @@ class CarBody:
         tau_O = mtv(R, cross(mv(R, COM), F))
         return F, tau_O, tau_L, tau_R, tau_c
 
-    def _solve_contacts(self, R, Rb, loads):
+    def _solve_contacts(self, R, Rb, loads, f0=None):
         """Projected Gauss-Seidel on plain M (like mj_fwdConstraint); returns per-point forces (n,5,3)
-        in the frame (t1 = world x, t2 = world y, n = world z)."""
+        in the frame (t1 = world x, t2 = world y, n = world z).  f0: forces to start from (warm start,
+        N_SWEEPS_WARM sweeps; contacts that are not active now start from zero), None: cold."""
         n = self.n
         f = np.zeros((n, 5, 3))
         if not self.contacts_enabled:
@@ -276,7 +280,12 @@ class CarBody:
                 afree_row = self._row_jacobian_apply(R, Rb, rO, rB, bodies[c], dvec, *a_free)
                 rows.append((c, k, rO, rB, dvec, col, Aii, Rreg, afree_row - aref))
         a_c = [np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 2)), np.zeros((n, 3))]
-        for _ in range(N_SWEEPS):
+        if f0 is not None:
+            f = np.where(active[:, :, None], f0, 0.0)
+            for (c, k, rO, rB, dvec, col, Aii, Rreg, resid0) in rows:
+                for q in range(4):
+                    a_c[q] = a_c[q] + f[:, c, k][:, None] * col[q]
+        for _ in range(N_SWEEPS if f0 is None else N_SWEEPS_WARM):
             for (c, k, rO, rB, dvec, col, Aii, Rreg, resid0) in rows:
                 cur = f[:, c, k]
                 res = resid0 + self._row_jacobian_apply(R, Rb, rO, rB, bodies[c], dvec, *a_c) + Rreg * cur
@@ -315,11 +324,12 @@ class CarBody:
         return F, tau_O, tau_L, tau_R, tau_c
 
     # -- stepping -------------------------------------------------------------------------------------------
-    def substep(self):
+    def substep(self, warm=False):
+        """One mj_step.  warm: not the first substep of the env step (start the contact solve from last_forces)."""
         h = TIMESTEP
         R, Rb = quat_to_mat(self.quat), quat_to_mat(self.qb)
         loads = self._smooth_loads(R, Rb)
-        f = self._solve_contacts(R, Rb, loads)
+        f = self._solve_contacts(R, Rb, loads, self.last_forces if warm else None)
         self.last_forces = f
         vdot, wdot, sdot, wbdot = self._solve(R, Rb, *self._loads_with_contacts(R, Rb, loads, f), gyro=True, h=h)
         self.v = self.v + h * vdot
@@ -333,8 +343,8 @@ class CarBody:
 
     def step(self, action):
         self.ctrl[:] = np.clip(np.asarray(action, dtype=np.float64), -1.0, 1.0)
-        for _ in range(FRAME_SKIP):
-            self.substep()
+        for k in range(FRAME_SKIP):
+            self.substep(warm=k > 0)
 
     def pos(self):
         return self.p[:, :2].copy()
