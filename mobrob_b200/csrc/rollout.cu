@@ -242,42 +242,118 @@ extern "C" int mr_rollout(mr_env* env, const float* params, int64_t T, float* la
 }
 
 // ---------------------------------------------------------------------------------------------
-// Unfused rollout: the same collect_rollouts semantics as mr_rollout, built from the stand-alone
-// kernels (policy forward, env step) plus two small bookkeeping kernels.  Used for the car, whose
-// contact solver is too heavy to share a warp with the MLP, and as a cross-check of the fused kernel.
+// Unfused rollout: the same collect_rollouts semantics as mr_rollout from the stand-alone env-step kernel plus ONE
+// bookkeeping kernel per step.  Used for the car, whose contact solver is too heavy to share a warp with the MLP,
+// for envs with optional observation keys, and as a cross-check of the fused kernel.
 namespace mr {
 
-int policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
-                          float* logp, float* val, int64_t n, const uint8_t* mask, void* stream);   // policy.cu
+constexpr int RS_WARPS = 8;   // 88 KB of shared memory per block: two blocks = 16 warps per SM, 16 384 envs in one wave
+constexpr int RS_E = 8;
 
-__global__ void noise_kernel(float* __restrict__ eps, int64_t N, uint64_t seed, uint64_t ctr, int64_t env_offset) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const uint64_t g = (uint64_t)(env_offset + n);
-    uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32)),
-                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    float2 z = normal2(r.x, r.y);
-    reinterpret_cast<float2*>(eps)[n] = z;
-}
+struct StepArgs {
+    const float* params;
+    int O;
+    int64_t N, t;
+    int record;            // finish step t - 1: time-out bootstrap, reward row, episode ring, start flags
+    int forward;           // open step t: buffer rows, policy forward, sampling
+    float* last_obs;       // [N][O]  observation the env returned (in), unchanged
+    float* last_starts;    // [N]     _last_episode_starts (updated by the record half)
+    float* obs; float* act; float* rew; float* starts; float* val; float* logp;   // rollout buffer, [T][N][...]
+    float* last_val;       // [N]  (closing call: V of the final observation)
+    const float* eps;      // [T][N][2] host-supplied draws or NULL -> Philox
+    uint64_t seed, noise_offset;
+    int64_t env_offset;
+    float gamma;
+    // outputs of the env step t - 1
+    const float* rew_tmp; const uint8_t* done; const uint8_t* trunc; const float* term_obs;
+    const double* ep_ret_n; const int32_t* ep_len_n;
+    double* ep_r; int32_t* ep_l; unsigned long long* ep_count; int ring_cap;
+};
 
-// RolloutBuffer.add bookkeeping after the env step: time-out bootstrap, episode ring, start flags.
-__global__ void record_kernel(int64_t N, const float* __restrict__ rew_tmp, const uint8_t* __restrict__ done,
-                              const uint8_t* __restrict__ trunc, const float* __restrict__ term_val, float gamma,
-                              float* __restrict__ rew_out, float* __restrict__ last_starts,
-                              const double* __restrict__ ep_ret_n, const int32_t* __restrict__ ep_len_n,
-                              double* __restrict__ ep_r, int32_t* __restrict__ ep_l,
-                              unsigned long long* __restrict__ ep_count, int ring_cap) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float r = rew_tmp[n];
-    if (trunc[n]) r = __fadd_rn(r, __fmul_rn(gamma, term_val[n]));
-    rew_out[n] = r;
-    const bool d = done[n] != 0;
-    last_starts[n] = d ? 1.f : 0.f;
-    if (d) {
-        unsigned long long slot = atomicAdd(ep_count, 1ull) % (unsigned long long)ring_cap;
-        ep_r[slot] = ep_ret_n[n];
-        ep_l[slot] = ep_len_n[n];
+// Between two env steps: [RolloutBuffer.add bookkeeping of the step that just ran] + [policy forward, Gaussian
+// sample, log-prob and buffer rows of the step about to run], a warp per tile of 8 envs.  Replaces, per step, two
+// device-to-device copies, the noise kernel, the policy forward, the masked terminal-value forward and the record
+// kernel (6 launches, ~68 us of a 242 us car step) by one launch.
+__global__ void __launch_bounds__(RS_WARPS * 32) rollout_step_kernel(StepArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    const int O = A.O;
+    SmemW W = stage_weights(smem, A.params, O);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* obsT = smem + smem_w_floats(O) + warp * (MAX_OBS * RS_E + 128 * RS_E);
+    float* hbuf = obsT + MAX_OBS * RS_E;
+    __syncthreads();
+    const float sig0 = expf(W.logstd[0]), sig1 = expf(W.logstd[1]);
+    const int64_t n_tiles = (A.N + RS_E - 1) / RS_E;
+    const int e_of = lane / 3, j_of = lane - 3 * e_of;
+    for (int64_t tile = (int64_t)blockIdx.x * RS_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * RS_WARPS) {
+        const int64_t s0 = tile * RS_E;
+        const int rows = (int)min((int64_t)RS_E, A.N - s0);
+        const bool own = lane < rows;          // lane e owns env s0 + e for the per-env bookkeeping
+        const int64_t n = s0 + lane;
+        float start_flag = own ? A.last_starts[n] : 0.f;
+        if (A.record) {
+            const bool tr = own && A.trunc[n] != 0;
+            float r = own ? A.rew_tmp[n] : 0.f;
+            if (__any_sync(0xffffffffu, tr)) {   // reward += gamma * V(terminal_observation) where the episode timed out
+                for (int idx = lane; idx < RS_E * O; idx += 32) {
+                    const int e = idx / O, k = idx - e * O;
+                    obsT[k * RS_E + e] = e < rows ? A.term_obs[s0 * O + idx] : 0.f;
+                }
+                __syncwarp();
+                const float out = warp_mlp_forward<RS_E>(W, O, obsT, hbuf, lane);
+                const float tv = __shfl_sync(0xffffffffu, out, 3 * (lane % RS_E) + 2);
+                if (tr) r = __fadd_rn(r, __fmul_rn(A.gamma, tv));
+            }
+            if (own) {
+                A.rew[(A.t - 1) * A.N + n] = r;
+                const bool d = A.done[n] != 0;
+                start_flag = d ? 1.f : 0.f;
+                A.last_starts[n] = start_flag;
+                if (d) {
+                    const unsigned long long slot = atomicAdd(A.ep_count, 1ull) % (unsigned long long)A.ring_cap;
+                    A.ep_r[slot] = A.ep_ret_n[n];
+                    A.ep_l[slot] = A.ep_len_n[n];
+                }
+            }
+        }
+        // the observation the policy acts on: RolloutBuffer.add(obs) row + transposed tile for the forward
+        for (int idx = lane; idx < RS_E * O; idx += 32) {
+            const int e = idx / O, k = idx - e * O;
+            const float v = e < rows ? A.last_obs[s0 * O + idx] : 0.f;
+            obsT[k * RS_E + e] = v;
+            if (A.forward && e < rows) A.obs[(A.t * A.N + s0) * O + idx] = v;
+        }
+        __syncwarp();
+        const float out = warp_mlp_forward<RS_E>(W, O, obsT, hbuf, lane);
+        if (!A.forward) {   // closing call: values of the final observation
+            if (lane < 3 * RS_E && e_of < rows && j_of == 2) A.last_val[s0 + e_of] = out;
+            continue;
+        }
+        const bool live = lane < 3 * RS_E && e_of < rows;
+        float a = out, lp = 0.f;
+        if (live && j_of < 2) {
+            const int64_t ne = s0 + e_of;
+            float z;
+            if (A.eps) {
+                z = A.eps[(A.t * A.N + ne) * 2 + j_of];
+            } else {
+                const uint64_t g = (uint64_t)(A.env_offset + ne);
+                const uint64_t c = A.noise_offset + (uint64_t)A.t;
+                const uint4 rr = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)c, (uint32_t)(c >> 32)),
+                                            make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+                const float2 zz = normal2(rr.x, rr.y);
+                z = j_of == 0 ? zz.x : zz.y;
+            }
+            const float sig = j_of == 0 ? sig0 : sig1;
+            a = __fadd_rn(out, __fmul_rn(sig, z));
+            lp = normal_logprob(a, out, sig);
+            A.act[(A.t * A.N + ne) * 2 + j_of] = a;
+        }
+        const float lp1 = __shfl_down_sync(0xffffffffu, lp, 1);
+        if (live && j_of == 0) A.logp[A.t * A.N + s0 + e_of] = __fadd_rn(lp, lp1);
+        if (live && j_of == 2) A.val[A.t * A.N + s0 + e_of] = out;
+        if (own) A.starts[A.t * A.N + n] = start_flag;
+        __syncwarp();
     }
 }
 
@@ -295,46 +371,44 @@ extern "C" int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, f
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t N = env->n;
     const int O = mr_env_obs_dim(env);
-    // scratch (library-owned, one per env handle): rew_tmp f32, tv f32, eps 2 f32, done u8, trunc u8,
-    // term_obs O f32, ep_ret f64, ep_len i32, act_scratch 2 f32
-    const size_t per_env = 4 + 4 + 8 + 1 + 1 + (size_t)O * 4 + 8 + 4 + 8 + 16;
+    MR_REQUIRE(O <= MAX_OBS, "the policy kernels take observations of at most 32 floats");
+    // scratch (library-owned, one per env handle): what one env step hands to the next bookkeeping launch
+    const size_t per_env = 8 + (size_t)O * 4 + 4 + 4 + 1 + 1;
     if (!env->scratch) {
         DeviceGuard guard(env->device);
-        MR_CUDA(cudaMalloc(&env->scratch, per_env * N + 4096));
-        MR_CUDA(cudaMemsetAsync(env->scratch, 0, per_env * N + 4096, s));
+        MR_CUDA(cudaMalloc(&env->scratch, per_env * N + 8 * 256));
+        MR_CUDA(cudaMemsetAsync(env->scratch, 0, per_env * N + 8 * 256, s));
     }
     char* p = static_cast<char*>(env->scratch);
     auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~size_t(255); return r; };
     double* ep_ret_n = (double*)take(N * 8);
     float* term_obs = (float*)take(N * O * 4);
-    float* eps_t = (float*)take(N * 8);
-    float* act_tmp = (float*)take(N * 8);
     float* rew_tmp = (float*)take(N * 4);
-    float* tv = (float*)take(N * 4);
     int32_t* ep_len_n = (int32_t*)take(N * 4);
     uint8_t* done = (uint8_t*)take(N);
     uint8_t* trunc = (uint8_t*)take(N);
-    const int tb = 256, nb = ceil_div(N, tb);
-    for (int64_t t = 0; t < T; ++t) {
-        MR_CUDA(cudaMemcpyAsync(obs + t * N * O, last_obs, N * O * 4, cudaMemcpyDeviceToDevice, s));
-        MR_CUDA(cudaMemcpyAsync(starts + t * N, last_starts, N * 4, cudaMemcpyDeviceToDevice, s));
-        const float* e = eps ? eps + t * N * 2 : eps_t;
-        if (!eps) {
-            mr::noise_kernel<<<nb, tb, 0, s>>>(eps_t, N, seed, noise_offset + (uint64_t)t, env_offset);
-            MR_CHECK_LAUNCH();
-        }
-        int rc = mr_policy_forward(params, O, last_obs, e, act + t * N * 2, logp + t * N, val + t * N, N, stream);
-        if (rc != MR_OK) return rc;
-        rc = mr_env_step(env, act + t * N * 2, last_obs, rew_tmp, done, trunc, term_obs, ep_ret_n, ep_len_n, stream);
-        if (rc != MR_OK) return rc;
-        rc = mr::policy_forward_masked(params, O, term_obs, nullptr, act_tmp, nullptr, tv, N, trunc, stream);
-        if (rc != MR_OK) return rc;
-        mr::record_kernel<<<nb, tb, 0, s>>>(N, rew_tmp, done, trunc, tv, (float)gamma, rew + t * N, last_starts,
-                                           ep_ret_n, ep_len_n, ep_r, ep_l, ep_count, ring_cap);
+
+    const size_t smem = (smem_w_floats(O) + RS_WARPS * (MAX_OBS * RS_E + 128 * RS_E)) * sizeof(float);
+    static OncePerDevice once;
+    if (once.first())
+        MR_CUDA(cudaFuncSetAttribute(mr::rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    const int64_t tiles = (N + RS_E - 1) / RS_E;
+    const int blocks = (int)std::min<int64_t>((tiles + RS_WARPS - 1) / RS_WARPS, (int64_t)sm_count() * 2);
+    StepArgs A;
+    A.params = params; A.O = O; A.N = N;
+    A.last_obs = last_obs; A.last_starts = last_starts;
+    A.obs = obs; A.act = act; A.rew = rew; A.starts = starts; A.val = val; A.logp = logp; A.last_val = last_val;
+    A.eps = eps; A.seed = seed; A.noise_offset = noise_offset; A.env_offset = env_offset; A.gamma = (float)gamma;
+    A.rew_tmp = rew_tmp; A.done = done; A.trunc = trunc; A.term_obs = term_obs; A.ep_ret_n = ep_ret_n; A.ep_len_n = ep_len_n;
+    A.ep_r = ep_r; A.ep_l = ep_l; A.ep_count = ep_count; A.ring_cap = ring_cap;
+    for (int64_t t = 0; t <= T; ++t) {
+        A.t = t; A.record = t > 0; A.forward = t < T;
+        mr::rollout_step_kernel<<<blocks, RS_WARPS * 32, smem, s>>>(A);
         MR_CHECK_LAUNCH();
+        if (t == T) break;
+        const int rc = mr_env_step(env, act + t * N * 2, last_obs, rew_tmp, done, trunc, term_obs, ep_ret_n, ep_len_n, stream);
+        if (rc != MR_OK) return rc;
     }
-    int rc = mr_policy_forward(params, O, last_obs, nullptr, act_tmp, nullptr, last_val, N, stream);
-    if (rc != MR_OK) return rc;
     MR_CUDA(cudaMemcpyAsync(last_done, done, N, cudaMemcpyDeviceToDevice, s));
     return MR_OK;
 }
