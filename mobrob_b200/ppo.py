@@ -616,6 +616,12 @@ class PPO:
             if "policy.optimizer.pth" in z.namelist():
                 opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu",
                                  weights_only=True)
+        obs_shape = data["observation_space"].get("_shape") or [0]
+        act_shape = data.get("action_space", {}).get("_shape") or [2]
+        if len(obs_shape) != 1 or not 0 < int(obs_shape[0]) < 32 or list(act_shape) != [2]:
+            # a robot outside the B200 path (doggo 58 -> 12, drone 12 -> 18, turtlebot3 43 -> 2): the archive can be
+            # inspected and re-saved (examples/fix_pickle_warning.py), not run
+            return StoredPolicy(path, data, sd, opt)
         plain = ("n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "ent_coef", "vf_coef",
                  "max_grad_norm", "normalize_advantage", "verbose", "seed")
         ctor = {k: data[k] for k in plain if k in data}
@@ -653,6 +659,46 @@ class PPO:
             up.exp_avg_sq.copy_(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(st))]))
             up.step[0] = int(st[0]["step"])
         return model
+
+
+class StoredPolicy:
+    """A policy zip whose observation / action shapes are outside the CUDA path (the reference's doggo, drone and
+    turtlebot3 policies): PPO.load returns this handle so that maintenance code like examples/fix_pickle_warning.py
+    (load_policy(...).save(...) over every robot) keeps working.  It holds the archive's contents and writes them
+    back in the same six-entry format; anything that would need the kernels raises."""
+
+    def __init__(self, path, data, state_dict, optimizer):
+        self.path, self.data, self.state_dict, self.optimizer = path, data, state_dict, optimizer
+        self.num_timesteps = data.get("num_timesteps", 0)
+        self.obs_shape = tuple(data["observation_space"].get("_shape") or ())
+        self.act_shape = tuple(data.get("action_space", {}).get("_shape") or ())
+
+    def save(self, path):
+        path = str(path)
+        if not path.endswith(".zip"):
+            path += ".zip"
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+
+        def pth(obj):
+            bio = io.BytesIO()
+            torch.save(obj, bio)
+            return bio.getvalue()
+
+        entries = [("data", json.dumps(self.data, indent=4)), ("pytorch_variables.pth", pth({})),
+                   ("policy.pth", pth(dict(self.state_dict))), ("policy.optimizer.pth", pth(self.optimizer or {})),
+                   ("_stable_baselines3_version", SB3_VERSION),
+                   ("system_info.txt", f"- mobrob_b200 (B200-native), archive passed through\n- PyTorch: {torch.__version__}\n")]
+        tmp = path + ".tmp"
+        with zipfile.ZipFile(tmp, "w") as z:   # the source may be the destination (fix_pickle_warning.py saves in place)
+            for name, blob in entries:
+                z.writestr(name, blob)
+        os.replace(tmp, path)
+
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError(f"{os.path.basename(self.path)}: observations {self.obs_shape} -> actions {self.act_shape} "
+                                  "are outside the B200 path (point and car; SURVEY.md section 2)")
+
+    predict = learn = train = collect_rollouts = set_env = _out_of_scope
 
 
 def _stored_schedule(entry, what):

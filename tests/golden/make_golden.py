@@ -13,7 +13,7 @@ Outputs:
   * ``kat2.json``                 mu / V of the shipped policy on _last_obs (torch CPU fp32)
   * ``policies/{env}-ppo.zip``    byte copy of the shipped artefact (load/save tests)
   * ``ref_rng.json``              a few draws of the reference RNG streams (numpy)
-  * ``examples/{train,control}.py``  byte copies of the reference's example scripts: INPUTS of
+  * ``examples/{train,control,fix_pickle_warning}.py``  byte copies of the reference's example scripts: INPUTS of
                                   tests/test_examples_gpu.py, which runs them unchanged through
                                   shims/ (they are fixtures, not product code -- nothing imports them)
   * ``kat4_ep_info.json``         the 100 most recent training episodes (r, l) stored in the shipped
@@ -72,7 +72,7 @@ def main():
 
     # the example scripts, byte for byte
     os.makedirs(os.path.join(HERE, "examples"), exist_ok=True)
-    for name in ("train.py", "control.py"):
+    for name in ("train.py", "control.py", "fix_pickle_warning.py"):
         shutil.copyfile(f"{REF}/examples/{name}", os.path.join(HERE, "examples", name))
 
     # KAT-4: Monitor's episode records of the reference's own training run

@@ -87,3 +87,51 @@ def test_control_script_runs_unchanged(cuda_lib, tmp_path, golden_dir):
     # the shipped policy reaches a goal every ~80-120 steps: >= 5 goals x (+5 bonus + progress) per 1000 steps
     assert float(m.group(1)) > 25.0, out.stdout[-500:]
     assert "rewards: [" in out.stdout
+
+
+def test_fix_pickle_warning_script_runs_unchanged(cuda_lib, tmp_path, golden_dir):
+    """examples/fix_pickle_warning.py:1-20: load_policy + save over all five robots.  point / car go through the CUDA
+    PPO object; doggo, drone and turtlebot3 (observations 58 / 12 / 43, actions 12 / 18 / 2: outside the path) come
+    back as archive handles that re-save what they hold and refuse to run.  The three out-of-scope zips here are
+    stand-ins with the shipped shapes, built from the point zip's entries."""
+    import io
+    import json
+    import zipfile
+
+    import torch
+
+    from mobrob_b200.ppo import PPO, StoredPolicy
+
+    pol = tmp_path / "policies"
+    os.makedirs(pol)
+    for name in ("point", "car"):
+        shutil.copyfile(os.path.join(golden_dir, "policies", f"{name}-ppo.zip"), pol / f"{name}-ppo.zip")
+    with zipfile.ZipFile(os.path.join(golden_dir, "policies", "point-ppo.zip")) as z:
+        data = json.loads(z.read("data"))
+    for name, (o, a) in {"doggo": (58, 12), "drone": (12, 18), "turtlebot3": (43, 2)}.items():
+        d = json.loads(json.dumps(data))
+        d["observation_space"]["_shape"] = [o]
+        d["action_space"]["_shape"] = [a]
+        sd = {"log_std": torch.zeros(a), "mlp_extractor.policy_net.0.weight": torch.randn(64, o), "action_net.weight": torch.randn(a, 64)}
+        bio = io.BytesIO()
+        torch.save(sd, bio)
+        with zipfile.ZipFile(pol / f"{name}-ppo.zip", "w") as z:
+            z.writestr("data", json.dumps(d))
+            z.writestr("policy.pth", bio.getvalue())
+            z.writestr("_stable_baselines3_version", "2.0.0")
+    out = _run("fix_pickle_warning.py", [], tmp_path)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    for name in ("point", "car"):
+        m = PPO.load(str(pol / f"{name}-ppo.zip"))
+        ref = PPO.load(os.path.join(golden_dir, "policies", f"{name}-ppo.zip"))
+        assert isinstance(m, PPO) and m.num_timesteps == ref.num_timesteps
+        for k, v in ref.policy.state_dict().items():
+            assert torch.equal(v, m.policy.state_dict()[k]), k
+    for name, o in (("doggo", 58), ("drone", 12), ("turtlebot3", 43)):
+        m = PPO.load(str(pol / f"{name}-ppo.zip"))
+        assert isinstance(m, StoredPolicy) and m.obs_shape == (o,)
+        assert sorted(zipfile.ZipFile(pol / f"{name}-ppo.zip").namelist()) == sorted(
+            ["data", "pytorch_variables.pth", "policy.pth", "policy.optimizer.pth", "_stable_baselines3_version", "system_info.txt"])
+        assert m.state_dict["mlp_extractor.policy_net.0.weight"].shape == (64, o)
+        with pytest.raises(NotImplementedError):
+            m.predict(None)
