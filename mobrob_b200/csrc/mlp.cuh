@@ -11,6 +11,13 @@
 
 namespace mr {
 
+#ifndef MR_MLP_UNROLL1
+#define MR_MLP_UNROLL1 2
+#endif
+#ifndef MR_MLP_UNROLL2
+#define MR_MLP_UNROLL2 8
+#endif
+constexpr int MLP_UNROLL1 = MR_MLP_UNROLL1, MLP_UNROLL2 = MR_MLP_UNROLL2;   // k-loops of the two hidden layers
 constexpr int HID = 64;
 constexpr int ACT = 2;
 constexpr int MAX_OBS = 32;
@@ -132,6 +139,7 @@ __device__ __forceinline__ float warp_mlp_forward(const SmemW& W, int O, const f
 #pragma unroll
         for (int e = 0; e < E; ++e) { acc[0][e] = b.x; acc[1][e] = b.y; acc[2][e] = b.z; acc[3][e] = b.w; }
     }
+#pragma unroll MLP_UNROLL1
     for (int k = 0; k < O; ++k) {
         float4 w = W.w1p[k * 32 + lane];
         float x[E];
@@ -166,7 +174,7 @@ __device__ __forceinline__ float warp_mlp_forward(const SmemW& W, int O, const f
 #pragma unroll
         for (int e = 0; e < E; ++e) { acc[0][e] = b.x; acc[1][e] = b.y; acc[2][e] = b.z; acc[3][e] = b.w; }
     }
-#pragma unroll 4
+#pragma unroll MLP_UNROLL2
     for (int k = 0; k < HID; ++k) {
         float4 w = W.w2p[k * 32 + lane];
         float hp[E], hv[E];
@@ -193,10 +201,18 @@ __device__ __forceinline__ float warp_mlp_forward(const SmemW& W, int O, const f
         int e = lane / 3, j = lane - 3 * e;
         const float* hw = W.headw + j * 64;
         const float* h = hbuf + (j == 2 ? 64 * E : 0) + e;
-        float s = W.headb[j];
-#pragma unroll 8
-        for (int u = 0; u < HID; ++u) s = fmaf(hw[u], h[u * E], s);
-        out = s;
+        // eight partial sums: one 64-term chain of dependent FMAs (each behind two shared-memory loads) was 12 % of the
+        // rollout kernel's stall samples
+        float s[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = 0.f;
+        s[0] = W.headb[j];
+#pragma unroll
+        for (int u = 0; u < HID; u += 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = fmaf(hw[u + i], h[(u + i) * E], s[i]);
+        }
+        out = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     }
     __syncwarp();
     return out;

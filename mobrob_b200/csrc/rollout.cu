@@ -83,15 +83,23 @@ __global__ void __launch_bounds__(RO_WARPS * 32) point_rollout_kernel(RolloutArg
     __syncwarp();
 
     const int e_of = lane / 3, j_of = lane - 3 * e_of;
+    // where element lane + 32 i of the tile's contiguous rows sits in the transposed tile (the division by the
+    // run-time O inside the step loop was 4 % of the kernel's stall samples)
+    constexpr int ROW_PASSES = (RO_E * MAX_OBS + 31) / 32;
+    int tile_off[ROW_PASSES];
+#pragma unroll
+    for (int i = 0; i < ROW_PASSES; ++i) {
+        const int idx = lane + 32 * i, e = idx / O, k = idx - e * O;
+        tile_off[i] = idx < n_live * O ? k * RO_E + e : -1;
+    }
     bool done_flag = false;
     for (int64_t t = 0; t < A.T; ++t) {
-        // RolloutBuffer.add(obs): the tile's 8 rows are contiguous in the [T][N][O] buffer
+        // RolloutBuffer.add(obs): the tile's rows are contiguous in the [T][N][O] buffer
         {
             float* dst = A.obs + (t * A.N + n0) * O;
-            for (int idx = lane; idx < n_live * O; idx += 32) {
-                int e = idx / O, k = idx - e * O;
-                dst[idx] = obsT[k * RO_E + e];
-            }
+#pragma unroll
+            for (int i = 0; i < ROW_PASSES; ++i)
+                if (tile_off[i] >= 0) dst[lane + 32 * i] = obsT[tile_off[i]];
         }
         float out = warp_mlp_forward<RO_E>(W, O, obsT, hbuf, lane);
         // sample: a = mu + sigma * eps ; log-prob in torch's evaluation order
