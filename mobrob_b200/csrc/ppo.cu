@@ -478,15 +478,24 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned n_cta) {
+// Split barrier: work placed between arrive and wait runs under the barrier's latency (~1 us).
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& target, unsigned n_cta) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += n_cta;
         // arrive = one release-reduction (no return value to wait for: the first poll leaves right behind it)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned target) {
+    if (threadIdx.x == 0) {
         while (ld_acquire_gpu(counter) < target) {}
     }
     __syncthreads();
+}
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned n_cta) {
+    grid_arrive(counter, target, n_cta);
+    grid_wait(counter, target);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -593,13 +602,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
                 bulk_wait_all();
             }
         }
-        if (m + 1 < n_mb) MK = tc::mb_const(E.stats, m + 1, A.normalize_adv);   // loads land under the barrier
         MR_TR(3);
-        grid_barrier(E.barrier, target, G);
-        MR_TR(4);
+        grid_arrive(E.barrier, target, G);
+        // the next minibatch's constants (two L2 loads, an fp64 division and a square root): after the arrive, so
+        // that they cost nothing in front of the barrier (2 % of the stall samples sat on them there)
+        if (m + 1 < n_mb) MK = tc::mb_const(E.stats, m + 1, A.normalize_adv);
+        // ... and this step's fp64 scalars of Adam
         ++step;
         b1pow *= (double)E.beta1;   // beta^step, carried from one pow() per launch
         b2pow *= (double)E.beta2;
+        tc::AdamK K;
+        K.beta1 = E.beta1; K.beta2 = E.beta2; K.omb1 = 1.f - E.beta1; K.omb2 = 1.f - E.beta2;
+        K.neg_step_size = (float)(-(double)E.lr / (1.0 - b1pow));
+        K.bc2_sqrt = (float)sqrt(1.0 - b2pow);
+        K.eps = E.eps;
+        const float ent_loss = entropy_loss_of(C.p_hs[2], C.p_hs[3]);   // (policy tower) the log_std this minibatch used
+        grid_wait(E.barrier, target);
+        MR_TR(4);
 
         const float* src = accb;
         if (E.X.world > 1) {
@@ -685,12 +704,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) ppo_epoch_tc_kernel(EpochArgs 
         tc::BlockRegs gOwn, gOth;
         tc::load_block(src + (size_t)C.tower * TL.size, TL, gOwn);
         tc::load_block(src + (size_t)(C.tower ^ 1) * TL.size, TL, gOth);
-        const float ent_loss = entropy_loss_of(C.p_hs[2], C.p_hs[3]);   // (policy tower) the log_std this minibatch used
-        tc::AdamK K;   // the step's fp64 scalars: evaluated while the loads are in flight
-        K.beta1 = E.beta1; K.beta2 = E.beta2; K.omb1 = 1.f - E.beta1; K.omb2 = 1.f - E.beta2;
-        K.neg_step_size = (float)(-(double)E.lr / (1.0 - b1pow));
-        K.bc2_sqrt = (float)sqrt(1.0 - b2pow);
-        K.eps = E.eps;
         MR_TR(30);
         double sq = tc::finish_block(gOwn, TL, C.tower == 0, E.G.ent_coef) + tc::finish_block(gOth, TL, C.tower != 0, E.G.ent_coef);
 #pragma unroll
