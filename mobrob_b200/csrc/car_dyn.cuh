@@ -51,6 +51,11 @@ constexpr int NSTATE = 24;  // p3 quat4 v3 w3 th2 s2 qb4 wb3
 struct Consts {
     double mass, com[3], JO[9], I_ax, I_s, Jinv0[9], JinvH[9];
     double posWL[3], posWR[3], posC[3];
+    // quotients of the constants above, [0]: h = 0, [1]: h = H (an fp64 division costs ~30 dependent instructions and
+    // the kernel formed these eleven per solve: 6 % of its stall samples)
+    double inv_mass, inv_Iax, inv_Is;
+    double ka[2], ks[2];     // I / (I + h d) of a wheel about its axle / of the caster
+    double iw[2], isd[2];    // 1 / (I + h d)
 };
 
 struct State {
@@ -115,8 +120,8 @@ struct Bias {
 // (M + h D) qacc = loads, h in {0, H}.  GYRO adds the bias terms.
 template <bool IMPLICIT, bool GYRO>
 __device__ inline void solve(const Consts& K, const Loads& L, const Bias& B, Gen& o) {
-    constexpr double h = IMPLICIT ? H : 0.0;
-    const double ka = K.I_ax / (K.I_ax + h * D_ROT), ks = K.I_s / (K.I_s + h * D_ROT);
+    constexpr int hv = IMPLICIT ? 1 : 0;
+    const double ka = K.ka[hv], ks = K.ks[hv];
     double rhs1[3], rhs2[3], t[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -129,10 +134,10 @@ __device__ inline void solve(const Consts& K, const Loads& L, const Bias& B, Gen
     for (int i = 0; i < 3; ++i) t[i] = rhs2[i] - t[i];
     mat3v(IMPLICIT ? K.JinvH : K.Jinv0, t, o.wd);
     cross3(o.wd, K.com, t);
-    const double im = 1.0 / K.mass;
+    const double im = K.inv_mass;
 #pragma unroll
     for (int i = 0; i < 3; ++i) o.a[i] = rhs1[i] * im - t[i];
-    const double iw = 1.0 / (K.I_ax + h * D_ROT), is = 1.0 / (K.I_s + h * D_ROT);
+    const double iw = K.iw[hv], is = K.isd[hv];
     o.sd[0] = (L.tL - K.I_ax * o.wd[0]) * iw;
     o.sd[1] = (L.tR - K.I_ax * o.wd[0]) * iw;
 #pragma unroll
@@ -149,13 +154,16 @@ __host__ __device__ constexpr int body_of(int k) { return k < 4 ? (k >> 1) : 2; 
 
 // Geometry of candidate contact k at the current pose (zB = world z in the chassis frame, pz = body height).
 // Cheap (~40 flops), so it is recomputed where needed instead of kept alive across the sweeps.
+// 1 / |zB projected normal to the axle|: the same for the four rim points (a square root and a division per call before)
+__device__ __forceinline__ double rim_scale(const double* zB) {
+    const double dn = sqrt(zB[1] * zB[1] + zB[2] * zB[2]);
+    return 1.0 / fmax(dn, 1e-12);
+}
 template <int k>
-__device__ __forceinline__ Contact contact_geometry(const Consts& K, const double* zB, double pz) {
+__device__ __forceinline__ Contact contact_geometry(const Consts& K, const double* zB, double pz, double dn) {
     Contact c;
     double pt[3], ctr[3];
     if (k < 4) {
-        double dn = sqrt(zB[1] * zB[1] + zB[2] * zB[2]);
-        dn = 1.0 / fmax(dn, 1e-12);
         const double d[3] = {0.0, -zB[1] * dn, -zB[2] * dn};  // most downward direction normal to the axle
         const double* pw = (k < 2) ? K.posWL : K.posWR;
         const double end = (k & 1) ? HALF_LEN : -HALF_LEN;
@@ -274,11 +282,11 @@ __device__ __forceinline__ void point_acc(const Contact& c, int body, const Gen&
 // Contact j's part of the set-up: its blocks (i <= j, j) of A, its right-hand sides and regularisers.
 template <int cj>
 __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, const Frame& F, const Gen& vel, const Gen& a_free,
-                                              const Scratch& S) {
+                                              const Scratch& S, double dn) {
     const double zB[3] = {F.R[6], F.R[7], F.R[8]};
-    const Contact ct = contact_geometry<cj>(K, zB, s.p[2]);
+    const Contact ct = contact_geometry<cj>(K, zB, s.p[2], dn);
     constexpr int body = body_of(cj);
-    const double im = 1.0 / K.mass, iax = 1.0 / K.I_ax, is = 1.0 / K.I_s;
+    const double im = K.inv_mass, iax = K.inv_Iax, is = K.inv_Is;
     const double rc[3] = {ct.rO[0] - K.com[0], ct.rO[1] - K.com[1], ct.rO[2] - K.com[2]};
     // T = [rc]x - (caster) [rB]x - (wheel) xhat xhat^T [rB]x ; e = rotor centre - com
     const double ex = rc[0] - ct.rB[0], ey = rc[1] - ct.rB[1], ez = rc[2] - ct.rB[2];
@@ -373,13 +381,14 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
 #pragma unroll
     for (int i = 0; i < N_ROWS; ++i) fl[i] = 0.0;
     unsigned active = 0u;
+    const double zB[3] = {F.R[6], F.R[7], F.R[8]};
+    const double dn = rim_scale(zB);
     if (contacts) {
-        const double zB[3] = {F.R[6], F.R[7], F.R[8]};
-        active |= contact_geometry<0>(K, zB, s.p[2]).active ? 1u : 0u;
-        active |= contact_geometry<1>(K, zB, s.p[2]).active ? 2u : 0u;
-        active |= contact_geometry<2>(K, zB, s.p[2]).active ? 4u : 0u;
-        active |= contact_geometry<3>(K, zB, s.p[2]).active ? 8u : 0u;
-        active |= contact_geometry<4>(K, zB, s.p[2]).active ? 16u : 0u;
+        active |= contact_geometry<0>(K, zB, s.p[2], dn).active ? 1u : 0u;
+        active |= contact_geometry<1>(K, zB, s.p[2], dn).active ? 2u : 0u;
+        active |= contact_geometry<2>(K, zB, s.p[2], dn).active ? 4u : 0u;
+        active |= contact_geometry<3>(K, zB, s.p[2], dn).active ? 8u : 0u;
+        active |= contact_geometry<4>(K, zB, s.p[2], dn).active ? 16u : 0u;
     }
     if (!active) {
 #pragma unroll
@@ -390,11 +399,11 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
         Gen a_free, vel;
         solve<false, true>(K, F.smooth, F.B, a_free);
         gen_velocity(s, F.R, vel);
-        contact_setup<0>(K, s, F, vel, a_free, S);
-        contact_setup<1>(K, s, F, vel, a_free, S);
-        contact_setup<2>(K, s, F, vel, a_free, S);
-        contact_setup<3>(K, s, F, vel, a_free, S);
-        contact_setup<4>(K, s, F, vel, a_free, S);
+        contact_setup<0>(K, s, F, vel, a_free, S, dn);
+        contact_setup<1>(K, s, F, vel, a_free, S, dn);
+        contact_setup<2>(K, s, F, vel, a_free, S, dn);
+        contact_setup<3>(K, s, F, vel, a_free, S, dn);
+        contact_setup<4>(K, s, F, vel, a_free, S, dn);
     }
     // Sweeps: rows in the order (normal, x, y) of every active contact.  The residuals r_j = resid0_j + sum A_jk f_k
     // are carried in registers and updated by the CHANGE of each force (15 independent multiply-adds, off the
@@ -446,9 +455,10 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
 }
 
 template <int c>
-__device__ __forceinline__ void add_contact_load(const Consts& K, const State& s, const Frame& F, const double (&fl)[N_ROWS], Loads& L) {
+__device__ __forceinline__ void add_contact_load(const Consts& K, const State& s, const Frame& F, const double (&fl)[N_ROWS], Loads& L,
+                                                 double dn) {
     const double zB[3] = {F.R[6], F.R[7], F.R[8]};
-    const Contact ct = contact_geometry<c>(K, zB, s.p[2]);
+    const Contact ct = contact_geometry<c>(K, zB, s.p[2], dn);
     constexpr int body = body_of(c);
     // force in chassis frame: sum_k f_k * (world axis k in chassis frame)
     double fb[3], t[3];
@@ -467,11 +477,13 @@ __device__ inline void add_contact_loads(const Consts& K, const State& s, const 
                                          const double (&fl)[N_ROWS], Loads& L) {
     L = F.smooth;
     if (!active) return;
-    if (active & 1u) add_contact_load<0>(K, s, F, fl, L);
-    if (active & 2u) add_contact_load<1>(K, s, F, fl, L);
-    if (active & 4u) add_contact_load<2>(K, s, F, fl, L);
-    if (active & 8u) add_contact_load<3>(K, s, F, fl, L);
-    if (active & 16u) add_contact_load<4>(K, s, F, fl, L);
+    const double zB[3] = {F.R[6], F.R[7], F.R[8]};
+    const double dn = rim_scale(zB);
+    if (active & 1u) add_contact_load<0>(K, s, F, fl, L, dn);
+    if (active & 2u) add_contact_load<1>(K, s, F, fl, L, dn);
+    if (active & 4u) add_contact_load<2>(K, s, F, fl, L, dn);
+    if (active & 8u) add_contact_load<3>(K, s, F, fl, L, dn);
+    if (active & 16u) add_contact_load<4>(K, s, F, fl, L, dn);
 }
 
 // warm: this is not the first substep of the env step (the scratch holds the previous substep's contact forces)

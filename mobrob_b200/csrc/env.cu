@@ -427,9 +427,12 @@ car::Consts make_car_consts() {
     }
     K.mass = msum + 2 * mw + mc;
     for (int k = 0; k < 3; ++k) K.com[k] = mom[k] / K.mass;
+    K.inv_mass = 1.0 / K.mass; K.inv_Iax = 1.0 / K.I_ax; K.inv_Is = 1.0 / K.I_s;
     for (int variant = 0; variant < 2; ++variant) {
         const double h = variant ? car::H : 0.0;
         const double ka = K.I_ax / (K.I_ax + h * car::D_ROT), ks = K.I_s / (K.I_s + h * car::D_ROT);
+        K.ka[variant] = ka; K.ks[variant] = ks;
+        K.iw[variant] = 1.0 / (K.I_ax + h * car::D_ROT); K.isd[variant] = 1.0 / (K.I_s + h * car::D_ROT);
         double Jc[9];
         for (int k = 0; k < 9; ++k) Jc[k] = K.JO[k];
         Jc[0] -= 2 * ka * K.I_ax;
