@@ -423,9 +423,9 @@ EP_D2H_BYTES = 100 * 12 + 8
 
 
 # dram bytes of one ppo_epoch_tc_kernel launch of the default workload by epochs per launch (ncu --set full,
-# profiles/r02_ncu_full.txt): 10 epochs 1157.5 MB read + 4.7 MB written (the 116 MB of records partly stay in the
+# profiles/r02_ncu_full.txt): 10 epochs 1145.2 MB read + 7.6 MB written (the 116 MB of records partly stay in the
 # 126 MB L2 from one epoch to the next); a single-epoch launch 154.2 MB + 3.9 MB
-UPDATE_KERNEL_DRAM_BYTES = {10: 1162.2e6, 1: 158.05e6}
+UPDATE_KERNEL_DRAM_BYTES = {10: 1152.8e6, 1: 158.05e6}
 ENV_STEP_DRAM_BYTES = 808.1e6      # 318.8 MB read + 489.3 MB written at 2^22 envs (profiles/r01_env_step_ncu_final.txt)
 
 
