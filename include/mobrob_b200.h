@@ -255,8 +255,10 @@ int mr_ppo_epoch_fused(float* params, float* exp_avg, float* exp_avg_sq, int64_t
                        float beta1, float beta2, float eps, float max_grad_norm, float* partials,
                        float* grad, float* info, mr_xchg* xchg, void* stream);
 
-/* Same contract as mr_rollout, built from the stand-alone kernels (policy forward, env step, two
- * bookkeeping kernels per step).  Works for both env kinds; the car uses this path. */
+/* Same contract as mr_rollout, from the stand-alone env-step kernel plus ONE kernel between two env steps (the
+ * finished step's RolloutBuffer.add bookkeeping -- time-out bootstrap, reward row, Monitor ring, start flags -- and
+ * the next step's policy forward, Gaussian sample and log-prob): 2 T + 1 launches.  Works for both env kinds and
+ * for envs with optional observation keys (rows of mr_env_obs_dim floats, at most 32); the car uses this path. */
 int mr_rollout_unfused(mr_env* env, const float* params, int64_t T, float* last_obs, float* last_starts,
                        float* obs, float* act, float* rew, float* starts, float* val, float* logp,
                        float* last_val, uint8_t* last_done, const float* eps, uint64_t seed,
