@@ -54,12 +54,15 @@ struct SmemW {
     const float4* w2p;  // [64][32]  same packing for the second layer
     const float4* b1p;  // [32]
     const float4* b2p;  // [32]
-    const float* headw; // [3][64]   action_net row 0, row 1, value_net row
+    const float* headw; // [3][HEAD_STRIDE]  action_net row 0, row 1, value_net row (rows 4 banks apart)
     const float* headb; // [4]       ab0 ab1 cb 0
     const float* logstd;// [4]
 };
 
-__host__ __device__ inline int smem_w_floats(int O) { return 128 * O + 8192 + 128 + 128 + 192 + 4 + 4; }
+// head weight rows 68 floats apart: with 64 the three rows sat in the same banks and the head loop's LDS.128 (12 lanes,
+// three rows) took 6 wavefronts each -- all of the rollout kernel's 40 M excess shared-memory wavefronts
+constexpr int HEAD_STRIDE = 68;
+__host__ __device__ inline int smem_w_floats(int O) { return 128 * O + 8192 + 128 + 128 + 208 + 4 + 4; }
 
 // One weight matrix of both towers, [64][K] row-major in global memory -> the packed image dst[k][lane]{4}.
 // A warp reads an 8-row x 4-column patch per pass (8 full sectors; the first form of this loop read one
@@ -86,7 +89,7 @@ __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ par
     float* b1 = w2 + 8192;
     float* b2 = b1 + 128;
     float* hw = b2 + 128;
-    float* hb = hw + 192;
+    float* hb = hw + 208;
     float* ls = hb + 4;
     stage_matrix(w1, params + L.pw1, params + L.vw1, O);
     stage_matrix(w2, params + L.pw2, params + L.vw2, HID);
@@ -97,7 +100,7 @@ __device__ inline SmemW stage_weights(float* smem, const float* __restrict__ par
         b2[idx] = __ldcg(params + ((j & 2) ? L.vb2 : L.pb2) + u);
     }
     for (int idx = threadIdx.x; idx < 192; idx += blockDim.x)
-        hw[idx] = idx < 128 ? __ldcg(params + L.aw + idx) : __ldcg(params + L.cw + idx - 128);
+        hw[(idx >> 6) * HEAD_STRIDE + (idx & 63)] = idx < 128 ? __ldcg(params + L.aw + idx) : __ldcg(params + L.cw + idx - 128);
     if (threadIdx.x < 4) {
         hb[threadIdx.x] = threadIdx.x < 2 ? __ldcg(params + L.ab + threadIdx.x)
                                           : (threadIdx.x == 2 ? __ldcg(params + L.cb) : 0.f);
@@ -199,7 +202,7 @@ __device__ __forceinline__ float warp_mlp_forward(const SmemW& W, int O, const f
     float out = 0.f;
     if (lane < 3 * E) {
         int e = lane / 3, j = lane - 3 * e;
-        const float* hw = W.headw + j * 64;
+        const float* hw = W.headw + j * HEAD_STRIDE;
         const float* h = hbuf + (j == 2 ? 64 * E : 0) + e;
         // eight partial sums: one 64-term chain of dependent FMAs (each behind two shared-memory loads) was 12 % of the
         // rollout kernel's stall samples
