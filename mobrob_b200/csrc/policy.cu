@@ -10,19 +10,9 @@ constexpr int PF_E = 8;
 __global__ void __launch_bounds__(PF_WARPS * 32)
 policy_forward_kernel(const float* __restrict__ params, int O, const float* __restrict__ obs,
                       const float* __restrict__ eps, float* __restrict__ act,
-                      float* __restrict__ logp, float* __restrict__ val, int64_t n,
-                      const uint8_t* __restrict__ mask) {
+                      float* __restrict__ logp, float* __restrict__ val, int64_t n) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (mask) {
-        // masked call (V(terminal_observation) of the rollout's time-out bootstrap): truncations are rare, so a block
-        // first looks whether any of its samples is flagged and leaves without staging the parameters if none is
-        bool any = false;
-        const int64_t per_pass = (int64_t)gridDim.x * PF_WARPS * PF_E;
-        for (int64_t s0 = ((int64_t)blockIdx.x * PF_WARPS + warp) * PF_E; s0 < n; s0 += per_pass)
-            any |= lane < PF_E && s0 + lane < n && mask[s0 + lane] != 0;
-        if (!__syncthreads_or(any)) return;
-    }
     SmemW W = stage_weights(smem, params, O);
     float* obsT = smem + smem_w_floats(O) + warp * (MAX_OBS * PF_E + 128 * PF_E);
     float* hbuf = obsT + MAX_OBS * PF_E;
@@ -33,7 +23,6 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
          tile += (int64_t)gridDim.x * PF_WARPS) {
         const int64_t s0 = tile * PF_E;
         const int rows = (int)min((int64_t)PF_E, n - s0);
-        if (mask && !__any_sync(0xffffffffu, lane < rows && mask[s0 + lane] != 0)) continue;
         // rows of the tile are contiguous in obs: coalesced read, transposed into obsT[k][e]
         for (int idx = lane; idx < PF_E * O; idx += 32) {
             int e = idx / O, k = idx - e * O;
@@ -61,20 +50,9 @@ policy_forward_kernel(const float* __restrict__ params, int O, const float* __re
 
 using namespace mr;
 
-namespace mr {
-// mr_policy_forward restricted to the samples whose mask byte is set (others' outputs are left untouched)
-int policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
-                          float* logp, float* val, int64_t n, const uint8_t* mask, void* stream);
-}
-
 extern "C" int mr_policy_forward(const float* params, int obs_dim, const float* obs,
                                  const float* eps, float* act, float* logp, float* val,
                                  int64_t n, void* stream) {
-    return mr::policy_forward_masked(params, obs_dim, obs, eps, act, logp, val, n, nullptr, stream);
-}
-
-int mr::policy_forward_masked(const float* params, int obs_dim, const float* obs, const float* eps, float* act,
-                              float* logp, float* val, int64_t n, const uint8_t* mask, void* stream) {
     MR_REQUIRE(params && obs && act, "NULL argument");
     MR_REQUIRE(obs_dim > 0 && obs_dim <= MAX_OBS, "obs_dim out of range");
     if (n <= 0) return MR_OK;
@@ -87,7 +65,7 @@ int mr::policy_forward_masked(const float* params, int obs_dim, const float* obs
     int64_t tiles = (n + PF_E - 1) / PF_E;
     int blocks = (int)std::min<int64_t>((tiles + PF_WARPS - 1) / PF_WARPS, (int64_t)sms * 2);
     policy_forward_kernel<<<blocks, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        params, obs_dim, obs, eps, act, logp, val, n, mask);
+        params, obs_dim, obs, eps, act, logp, val, n);
     MR_CHECK_LAUNCH();
     return MR_OK;
 }
