@@ -62,6 +62,72 @@ struct State {
     double p[3], q[4], v[3], w[3], th[2], s[2], qb[4], wb[3];
 };
 
+inline void inv3(const double* m, double* o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double id = 1.0 / det;
+    o[0] = (e * i - f * h) * id; o[1] = (c * h - b * i) * id; o[2] = (b * f - c * e) * id;
+    o[3] = (f * g - d * i) * id; o[4] = (a * i - c * g) * id; o[5] = (c * d - a * f) * id;
+    o[6] = (d * h - e * g) * id; o[7] = (b * g - a * h) * id; o[8] = (a * e - b * d) * id;
+}
+inline void add_shifted(double* J, double m, const double* Idiag, const double* d) {
+    const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            J[3 * r + c] += (r == c ? Idiag[r] + m * dd : 0.0) - m * d[r] * d[c];
+}
+
+// Mass properties of xmls/car.xml (density 5), on the host in double precision, by the formulas of oracle/car_oracle.py
+inline Consts make_consts() {
+    Consts K{};
+    const double rho = 5.0, pi = 3.141592653589793;
+    const double boxes[5][6] = {{.1, .1, .05, 0, 0, 0},      {.1, .01, .05, 0, .15, 0},   {.01, .025, .03, 0, .125, 0},
+                                {.05, .01, .05, 0, -.165, 0}, {.05, .03, .01, 0, -.13, .04}};
+    double msum = 0, mom[3] = {0, 0, 0};
+    for (auto& b : boxes) {
+        const double m = 8 * b[0] * b[1] * b[2] * rho;
+        const double I[3] = {m / 3 * (b[1] * b[1] + b[2] * b[2]), m / 3 * (b[0] * b[0] + b[2] * b[2]),
+                             m / 3 * (b[0] * b[0] + b[1] * b[1])};
+        add_shifted(K.JO, m, I, b + 3);
+        msum += m;
+        for (int k = 0; k < 3; ++k) mom[k] += m * b[3 + k];
+    }
+    const double mw = pi * R_WHEEL * R_WHEEL * (2 * HALF_LEN) * rho;
+    K.I_ax = 0.5 * mw * R_WHEEL * R_WHEEL;
+    const double itr = mw * (3 * R_WHEEL * R_WHEEL + (2 * HALF_LEN) * (2 * HALF_LEN)) / 12;
+    const double mc = 4.0 / 3.0 * pi * R_CASTER * R_CASTER * R_CASTER * rho;
+    K.I_s = 0.4 * mc * R_CASTER * R_CASTER;
+    const double wl[3] = {-.1 - .03, .1, -.05}, wr[3] = {.1 + .03, .1, -.05}, pc[3] = {0., -.1, -.05};
+    const double Iw[3] = {K.I_ax, itr, itr}, Is[3] = {K.I_s, K.I_s, K.I_s};
+    add_shifted(K.JO, mw, Iw, wl);
+    add_shifted(K.JO, mw, Iw, wr);
+    add_shifted(K.JO, mc, Is, pc);
+    for (int k = 0; k < 3; ++k) {
+        K.posWL[k] = wl[k]; K.posWR[k] = wr[k]; K.posC[k] = pc[k];
+        mom[k] += mw * (wl[k] + wr[k]) + mc * pc[k];
+    }
+    K.mass = msum + 2 * mw + mc;
+    for (int k = 0; k < 3; ++k) K.com[k] = mom[k] / K.mass;
+    K.inv_mass = 1.0 / K.mass; K.inv_Iax = 1.0 / K.I_ax; K.inv_Is = 1.0 / K.I_s;
+    for (int variant = 0; variant < 2; ++variant) {
+        const double h = variant ? H : 0.0;
+        const double ka = K.I_ax / (K.I_ax + h * D_ROT), ks = K.I_s / (K.I_s + h * D_ROT);
+        K.ka[variant] = ka; K.ks[variant] = ks;
+        K.iw[variant] = 1.0 / (K.I_ax + h * D_ROT); K.isd[variant] = 1.0 / (K.I_s + h * D_ROT);
+        double Jc[9];
+        for (int k = 0; k < 9; ++k) Jc[k] = K.JO[k];
+        Jc[0] -= 2 * ka * K.I_ax;
+        for (int k = 0; k < 3; ++k) Jc[4 * k] -= ks * K.I_s;
+        // + m [c]x [c]x = -m (|c|^2 1 - c c^T)
+        const double cc = K.com[0] * K.com[0] + K.com[1] * K.com[1] + K.com[2] * K.com[2];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Jc[3 * r + c] -= K.mass * ((r == c ? cc : 0.0) - K.com[r] * K.com[c]);
+        inv3(Jc, variant ? K.JinvH : K.Jinv0);
+    }
+    return K;
+}
+
+
 // chassis-frame generalised accelerations (or velocities -- the Jacobian is the same linear map)
 struct Gen {
     double a[3], wd[3], sd[2], ud[3];
@@ -87,14 +153,14 @@ __host__ __device__ inline void mat3tv(const double* M, const double* v, double*
     o[1] = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
     o[2] = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
 }
-__device__ inline void quat2mat(const double* q, double* R) {
+__host__ __device__ inline void quat2mat(const double* q, double* R) {
     const double w = q[0], x = q[1], y = q[2], z = q[3];
     R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
     R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
     R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
 }
 // mju_quatIntegrate: q <- normalise(q * exp(h w / 2)), w in the local frame
-__device__ inline void quat_integrate(double* q, const double* w, double h) {
+__host__ __device__ inline void quat_integrate(double* q, const double* w, double h) {
     const double nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     const double ang = nw * h;
     const double inv = 1.0 / fmax(nw, 1e-300);
@@ -119,7 +185,7 @@ struct Bias {
 
 // (M + h D) qacc = loads, h in {0, H}.  GYRO adds the bias terms.
 template <bool IMPLICIT, bool GYRO>
-__device__ inline void solve(const Consts& K, const Loads& L, const Bias& B, Gen& o) {
+__host__ __device__ inline void solve(const Consts& K, const Loads& L, const Bias& B, Gen& o) {
     constexpr int hv = IMPLICIT ? 1 : 0;
     const double ka = K.ka[hv], ks = K.ks[hv];
     double rhs1[3], rhs2[3], t[3];
@@ -155,12 +221,12 @@ __host__ __device__ constexpr int body_of(int k) { return k < 4 ? (k >> 1) : 2; 
 // Geometry of candidate contact k at the current pose (zB = world z in the chassis frame, pz = body height).
 // Cheap (~40 flops), so it is recomputed where needed instead of kept alive across the sweeps.
 // 1 / |zB projected normal to the axle|: the same for the four rim points (a square root and a division per call before)
-__device__ __forceinline__ double rim_scale(const double* zB) {
+__host__ __device__ __forceinline__ double rim_scale(const double* zB) {
     const double dn = sqrt(zB[1] * zB[1] + zB[2] * zB[2]);
     return 1.0 / fmax(dn, 1e-12);
 }
 template <int k>
-__device__ __forceinline__ Contact contact_geometry(const Consts& K, const double* zB, double pz, double dn) {
+__host__ __device__ __forceinline__ Contact contact_geometry(const Consts& K, const double* zB, double pz, double dn) {
     Contact c;
     double pt[3], ctr[3];
     if (k < 4) {
@@ -194,7 +260,7 @@ struct Frame {
 };
 
 // chassis-frame generalised velocity (the Jacobian maps it like an acceleration)
-__device__ inline void gen_velocity(const State& s, const double* R, Gen& vel) {
+__host__ __device__ inline void gen_velocity(const State& s, const double* R, Gen& vel) {
     double Rb[9], ub[3];
     quat2mat(s.qb, Rb);
     mat3v(Rb, s.wb, ub);
@@ -204,7 +270,7 @@ __device__ inline void gen_velocity(const State& s, const double* R, Gen& vel) {
     vel.ud[0] = ub[0]; vel.ud[1] = ub[1]; vel.ud[2] = ub[2];
 }
 
-__device__ inline void make_frame(const Consts& K, const State& s, double c0, double c1, Frame& F) {
+__host__ __device__ inline void make_frame(const Consts& K, const State& s, double c0, double c1, Frame& F) {
     quat2mat(s.q, F.R);
     double Rb[9], ub[3];
     quat2mat(s.qb, Rb);
@@ -241,13 +307,22 @@ __device__ inline void make_frame(const Consts& K, const State& s, double c0, do
 struct Scratch {
     uint32_t base;     // shared-window byte address of this thread's entry 0
     uint32_t stride;   // bytes between consecutive entries
-    __device__ __forceinline__ double ld(int e) const {
+    double* host;      // host build of these routines only (tests/host/car_dyn_host.cu): entry e is host[e]
+    __host__ __device__ __forceinline__ double ld(int e) const {
+#ifdef __CUDA_ARCH__
         double v;
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)e * stride));
         return v;
+#else
+        return host[e];
+#endif
     }
-    __device__ __forceinline__ void st(int e, double v) const {
+    __host__ __device__ __forceinline__ void st(int e, double v) const {
+#ifdef __CUDA_ARCH__
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + (uint32_t)e * stride), "d"(v) : "memory");
+#else
+        host[e] = v;
+#endif
     }
 };
 constexpr int N_ROWS = 15;                              // 5 contacts x (world x, world y, normal)
@@ -262,10 +337,10 @@ constexpr int SCRATCH_DOUBLES = SCR_FL + N_ROWS;        // 221 doubles = 1768 B 
 __host__ __device__ constexpr int a_index(int i, int j) {   // i <= j
     return i * N_ROWS - i * (i - 1) / 2 + (j - i);
 }
-__device__ __forceinline__ double a_get(const Scratch& S, int i, int j) { return i <= j ? S.ld(a_index(i, j)) : S.ld(a_index(j, i)); }
+__host__ __device__ __forceinline__ double a_get(const Scratch& S, int i, int j) { return i <= j ? S.ld(a_index(i, j)) : S.ld(a_index(j, i)); }
 
 // acceleration (velocity) of a contact point of `body` for chassis-frame generalised accelerations g, chassis frame
-__device__ __forceinline__ void point_acc(const Contact& c, int body, const Gen& g, double* acc) {
+__host__ __device__ __forceinline__ void point_acc(const Contact& c, int body, const Gen& g, double* acc) {
     double t[3];
     cross3(g.wd, c.rO, t);
     acc[0] = g.a[0] + t[0]; acc[1] = g.a[1] + t[1]; acc[2] = g.a[2] + t[2];
@@ -281,7 +356,7 @@ __device__ __forceinline__ void point_acc(const Contact& c, int body, const Gen&
 
 // Contact j's part of the set-up: its blocks (i <= j, j) of A, its right-hand sides and regularisers.
 template <int cj>
-__device__ __forceinline__ void contact_setup(const Consts& K, const State& s, const Frame& F, const Gen& vel, const Gen& a_free,
+__host__ __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, const Frame& F, const Gen& vel, const Gen& a_free,
                                               const Scratch& S, double dn) {
     const double zB[3] = {F.R[6], F.R[7], F.R[8]};
     const Contact ct = contact_geometry<cj>(K, zB, s.p[2], dn);
@@ -375,7 +450,7 @@ __device__ __forceinline__ void contact_setup(const Consts& K, const State& s, c
 // set persists from one 4 ms substep to the next, and 10 + 9 x 4 sweeps per env step end as close to the
 // converged forces as 10 x 10 cold ones did (tools/experiments/car_warm_start_probe.py).  Every solve leaves its
 // forces in the scratch.  Returns the mask of active contacts (0: fl is all zero).
-__device__ inline unsigned solve_contacts(const Consts& K, const State& s, const Frame& F, bool contacts, double (&fl)[N_ROWS],
+__host__ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const Frame& F, bool contacts, double (&fl)[N_ROWS],
                                           const Scratch& S, bool warm) {
 #pragma unroll
     for (int i = 0; i < N_ROWS; ++i) fl[i] = 0.0;
@@ -454,7 +529,7 @@ __device__ inline unsigned solve_contacts(const Consts& K, const State& s, const
 }
 
 template <int c>
-__device__ __forceinline__ void add_contact_load(const Consts& K, const State& s, const Frame& F, const double (&fl)[N_ROWS], Loads& L,
+__host__ __device__ __forceinline__ void add_contact_load(const Consts& K, const State& s, const Frame& F, const double (&fl)[N_ROWS], Loads& L,
                                                  double dn) {
     const double zB[3] = {F.R[6], F.R[7], F.R[8]};
     const Contact ct = contact_geometry<c>(K, zB, s.p[2], dn);
@@ -472,7 +547,7 @@ __device__ __forceinline__ void add_contact_load(const Consts& K, const State& s
     else { L.tc[0] += t[0]; L.tc[1] += t[1]; L.tc[2] += t[2]; }
 }
 
-__device__ inline void add_contact_loads(const Consts& K, const State& s, const Frame& F, unsigned active,
+__host__ __device__ inline void add_contact_loads(const Consts& K, const State& s, const Frame& F, unsigned active,
                                          const double (&fl)[N_ROWS], Loads& L) {
     L = F.smooth;
     if (!active) return;
@@ -486,7 +561,7 @@ __device__ inline void add_contact_loads(const Consts& K, const State& s, const 
 }
 
 // warm: this is not the first substep of the env step (the scratch holds the previous substep's contact forces)
-__device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts, const Scratch& S, bool warm) {
+__host__ __device__ inline void substep(const Consts& K, State& s, double c0, double c1, bool contacts, const Scratch& S, bool warm) {
     Frame F;
     make_frame(K, s, c0, c1, F);
     double fl[N_ROWS];
@@ -511,7 +586,7 @@ __device__ inline void substep(const Consts& K, State& s, double c0, double c1, 
 
 // Engine.obs(): sorted-key layout [accelerometer 0:3 | ballangvel_rear 3:6 | ballquat_rear (3x3) 6:15 |
 // goal_compass 15:17 | gyro 17:20 | magnetometer 20:23 | velocimeter 23:26]
-__device__ inline void sensors(const Consts& K, const State& s, double c0, double c1, float gx, float gy,
+__host__ __device__ inline void sensors(const Consts& K, const State& s, double c0, double c1, float gx, float gy,
                                bool contacts, float* o, const Scratch& S) {
     Frame F;
     make_frame(K, s, c0, c1, F);

@@ -381,70 +381,8 @@ __global__ void car_get_pos_kernel(CarSoA st, double* __restrict__ out) {
 }
 
 // ---- mass properties of car.xml (density 5), same formulas as oracle/car_oracle.py -----------------------
-static void inv3(const double* m, double* o) {
-    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
-    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-    const double id = 1.0 / det;
-    o[0] = (e * i - f * h) * id; o[1] = (c * h - b * i) * id; o[2] = (b * f - c * e) * id;
-    o[3] = (f * g - d * i) * id; o[4] = (a * i - c * g) * id; o[5] = (c * d - a * f) * id;
-    o[6] = (d * h - e * g) * id; o[7] = (b * g - a * h) * id; o[8] = (a * e - b * d) * id;
-}
 
-static void add_shifted(double* J, double m, const double* Idiag, const double* d) {
-    const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c)
-            J[3 * r + c] += (r == c ? Idiag[r] + m * dd : 0.0) - m * d[r] * d[c];
-}
-
-car::Consts make_car_consts() {
-    car::Consts K{};
-    const double rho = 5.0, pi = 3.141592653589793;
-    const double boxes[5][6] = {{.1, .1, .05, 0, 0, 0},      {.1, .01, .05, 0, .15, 0},   {.01, .025, .03, 0, .125, 0},
-                                {.05, .01, .05, 0, -.165, 0}, {.05, .03, .01, 0, -.13, .04}};
-    double msum = 0, mom[3] = {0, 0, 0};
-    for (auto& b : boxes) {
-        const double m = 8 * b[0] * b[1] * b[2] * rho;
-        const double I[3] = {m / 3 * (b[1] * b[1] + b[2] * b[2]), m / 3 * (b[0] * b[0] + b[2] * b[2]),
-                             m / 3 * (b[0] * b[0] + b[1] * b[1])};
-        add_shifted(K.JO, m, I, b + 3);
-        msum += m;
-        for (int k = 0; k < 3; ++k) mom[k] += m * b[3 + k];
-    }
-    const double mw = pi * car::R_WHEEL * car::R_WHEEL * (2 * car::HALF_LEN) * rho;
-    K.I_ax = 0.5 * mw * car::R_WHEEL * car::R_WHEEL;
-    const double itr = mw * (3 * car::R_WHEEL * car::R_WHEEL + (2 * car::HALF_LEN) * (2 * car::HALF_LEN)) / 12;
-    const double mc = 4.0 / 3.0 * pi * car::R_CASTER * car::R_CASTER * car::R_CASTER * rho;
-    K.I_s = 0.4 * mc * car::R_CASTER * car::R_CASTER;
-    const double wl[3] = {-.1 - .03, .1, -.05}, wr[3] = {.1 + .03, .1, -.05}, pc[3] = {0., -.1, -.05};
-    const double Iw[3] = {K.I_ax, itr, itr}, Is[3] = {K.I_s, K.I_s, K.I_s};
-    add_shifted(K.JO, mw, Iw, wl);
-    add_shifted(K.JO, mw, Iw, wr);
-    add_shifted(K.JO, mc, Is, pc);
-    for (int k = 0; k < 3; ++k) {
-        K.posWL[k] = wl[k]; K.posWR[k] = wr[k]; K.posC[k] = pc[k];
-        mom[k] += mw * (wl[k] + wr[k]) + mc * pc[k];
-    }
-    K.mass = msum + 2 * mw + mc;
-    for (int k = 0; k < 3; ++k) K.com[k] = mom[k] / K.mass;
-    K.inv_mass = 1.0 / K.mass; K.inv_Iax = 1.0 / K.I_ax; K.inv_Is = 1.0 / K.I_s;
-    for (int variant = 0; variant < 2; ++variant) {
-        const double h = variant ? car::H : 0.0;
-        const double ka = K.I_ax / (K.I_ax + h * car::D_ROT), ks = K.I_s / (K.I_s + h * car::D_ROT);
-        K.ka[variant] = ka; K.ks[variant] = ks;
-        K.iw[variant] = 1.0 / (K.I_ax + h * car::D_ROT); K.isd[variant] = 1.0 / (K.I_s + h * car::D_ROT);
-        double Jc[9];
-        for (int k = 0; k < 9; ++k) Jc[k] = K.JO[k];
-        Jc[0] -= 2 * ka * K.I_ax;
-        for (int k = 0; k < 3; ++k) Jc[4 * k] -= ks * K.I_s;
-        // + m [c]x [c]x = -m (|c|^2 1 - c c^T)
-        const double cc = K.com[0] * K.com[0] + K.com[1] * K.com[1] + K.com[2] * K.com[2];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) Jc[3 * r + c] -= K.mass * ((r == c ? cc : 0.0) - K.com[r] * K.com[c]);
-        inv3(Jc, variant ? K.JinvH : K.Jinv0);
-    }
-    return K;
-}
+car::Consts make_car_consts() { return car::make_consts(); }
 
 }  // namespace mr
 
