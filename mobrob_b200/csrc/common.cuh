@@ -10,6 +10,47 @@
 
 namespace mr {
 
+// Explicitly rounded fp64 operations and the 64 x 64 -> high 64 multiply: the device intrinsics, and plain IEEE
+// operations in the HOST builds of the __host__ __device__ routines (tests/host/*.cu; x86-64 without -mfma does not
+// contract a product and a sum).
+namespace rn {
+__host__ __device__ __forceinline__ double add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+__host__ __device__ __forceinline__ double sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+__host__ __device__ __forceinline__ double mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ double root(double a) {
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t mulhi(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+}  // namespace rn
+
 void set_error(const char* fmt, ...);
 void count_launch(uint64_t n = 1);
 
@@ -84,10 +125,10 @@ struct DeviceGuard {
 struct Pcg64 {
     uint64_t hi, lo, inc_hi, inc_lo;
 
-    __device__ __forceinline__ uint64_t next64() {
+    __host__ __device__ __forceinline__ uint64_t next64() {
         const uint64_t MH = 0x2360ED051FC65DA4ull, ML = 0x4385DF649FCCF645ull;
         uint64_t nlo = lo * ML;
-        uint64_t nhi = __umul64hi(lo, ML) + hi * ML + lo * MH;
+        uint64_t nhi = rn::mulhi(lo, ML) + hi * ML + lo * MH;
         uint64_t slo = nlo + inc_lo;
         uint64_t carry = slo < nlo ? 1ull : 0ull;
         hi = nhi + inc_hi + carry;
@@ -96,12 +137,12 @@ struct Pcg64 {
         unsigned rot = (unsigned)(hi >> 58);
         return (x >> rot) | (x << ((64u - rot) & 63u));
     }
-    __device__ __forceinline__ double next_double() {
+    __host__ __device__ __forceinline__ double next_double() {
         return (double)(next64() >> 11) * (1.0 / 9007199254740992.0);
     }
     // Generator.uniform(low, high): low + (high - low) * u, no contraction.
-    __device__ __forceinline__ double uniform(double low, double high) {
-        return __dadd_rn(low, __dmul_rn(__dsub_rn(high, low), next_double()));
+    __host__ __device__ __forceinline__ double uniform(double low, double high) {
+        return rn::add(low, rn::mul(rn::sub(high, low), next_double()));
     }
 };
 
@@ -113,7 +154,7 @@ struct Pcg64 {
 struct MtHead {
     uint32_t a, a1, b;
     int j;
-    __device__ explicit MtHead(uint32_t seed) {
+    __host__ __device__ explicit MtHead(uint32_t seed) {
         a = seed;
         a1 = 1812433253u * (a ^ (a >> 30)) + 1u;
         uint32_t x = a1;
@@ -121,7 +162,7 @@ struct MtHead {
         b = x;
         j = 0;
     }
-    __device__ uint32_t next32() {
+    __host__ __device__ uint32_t next32() {
         uint32_t y = (a & 0x80000000u) | (a1 & 0x7fffffffu);
         uint32_t v = b ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         a = a1;
@@ -134,26 +175,26 @@ struct MtHead {
         v ^= v >> 18;
         return v;
     }
-    __device__ double next_double() {
+    __host__ __device__ double next_double() {
         uint32_t x = next32() >> 5, y = next32() >> 6;
         return ((double)x * 67108864.0 + (double)y) / 9007199254740992.0;
     }
-    __device__ double uniform(double low, double high) {
-        return __dadd_rn(low, __dmul_rn(__dsub_rn(high, low), next_double()));
+    __host__ __device__ double uniform(double low, double high) {
+        return rn::add(low, rn::mul(rn::sub(high, low), next_double()));
     }
 };
 
 // Engine.reset -> build_layout -> build_world_config: the heading is the first uniform after
 // the robot xy pair and the accepted goal xy pair.
-__device__ inline double engine_heading(uint32_t engine_seed) {
+__host__ __device__ inline double engine_heading(uint32_t engine_seed) {
     MtHead rs(engine_seed);
     const double lo = -2 + 0.4, hi = 2 - 0.4;  // constrain_placement(extents, keepout)
     const double keep = 0.4 + 0.0 + 0.4;       // robot_keepout + margin + goal_keepout
     double rx = rs.uniform(lo, hi), ry = rs.uniform(lo, hi);
     for (int k = 0; k < 55; ++k) {
         double gx = rs.uniform(lo, hi), gy = rs.uniform(lo, hi);
-        double dx = __dsub_rn(gx, rx), dy = __dsub_rn(gy, ry);
-        double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        double dx = rn::sub(gx, rx), dy = rn::sub(gy, ry);
+        double dist = rn::root(rn::add(rn::mul(dx, dx), rn::mul(dy, dy)));
         if (!(dist < keep)) break;
     }
     return rs.uniform(0.0, 2 * 3.141592653589793);

@@ -71,7 +71,7 @@ struct CarSoA {
     }
 };
 
-__device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool full) {
+__host__ __device__ inline void car_reset(CarHot& h, const EnvCold& cold, int64_t i, bool full) {
     if (full) {
         // Engine.reset() once (wrapper.py:190); CarEnv.set_pos only rewrites qpos[0:2] (wrapper.py:320-326)
         int64_t seed = cold.engine_seed[i] + 1;
@@ -109,7 +109,7 @@ constexpr int CAR_OBS_PRE = 15;
 
 // data.qpos = free joint (pos, quat) + wheel angles + rear ball quat; data.qvel = free joint (linear world, angular
 // body) + wheel rates + ball angular velocity: the order of mr_env_get_state's reference view.
-__device__ inline void car_obs_ext(const CarHot& h, CarExt& x) {
+__host__ __device__ inline void car_obs_ext(const CarHot& h, CarExt& x) {
     const car::State& s = h.s;
     x.ctrl[0] = h.cx; x.ctrl[1] = h.cz;
     x.goal_dist = (float)exp(-point::dist2((double)h.gx, (double)h.gy, s.p[0], s.p[1]));
@@ -121,7 +121,7 @@ __device__ inline void car_obs_ext(const CarHot& h, CarExt& x) {
     x.qvel[6] = (float)s.s[0]; x.qvel[7] = (float)s.s[1];
 }
 
-__device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const EnvCold& cold, int64_t i,
+__host__ __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const EnvCold& cold, int64_t i,
                                           float a0, float a1, const EnvCfg& cfg, bool contacts, float* obs,
                                           float* term_obs, const car::Scratch& S, CarExt* ext = nullptr,
                                           CarExt* term_ext = nullptr) {
@@ -135,14 +135,14 @@ __device__ inline StepResult car_env_step(const car::Consts& K, CarHot& h, const
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.s.p[0], h.s.p[1]);
     r.reach = dcur < REACH_RADIUS;
-    double reward = __dsub_rn(dprev, dcur);
-    if (r.reach) reward = __dadd_rn(reward, REACH_BONUS);
+    double reward = rn::sub(dprev, dcur);
+    if (r.reach) reward = rn::add(reward, REACH_BONUS);
     h.elapsed += 1;
     const bool term = r.reach && cfg.terminate_on_goal;
     const bool tl = cfg.time_limit > 0 && h.elapsed >= cfg.time_limit;
     r.done = term || tl;
     r.trunc = tl && !term;
-    h.ep_ret = __dadd_rn(h.ep_ret, reward);
+    h.ep_ret = rn::add(h.ep_ret, reward);
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;

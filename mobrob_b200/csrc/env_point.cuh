@@ -38,7 +38,7 @@ __host__ __device__ inline int obs_dim_ext(int base, int nq, int nv, unsigned f)
 
 // BASE floats of the default row, PRE of them in front of goal_compass (= in front of "ctrl")
 template <int BASE, int PRE, int NQ, int NV>
-__device__ __forceinline__ void emit_obs_row(float* __restrict__ dst, const float* base, const ObsExt<NQ, NV>& x, unsigned f) {
+__host__ __device__ __forceinline__ void emit_obs_row(float* __restrict__ dst, const float* base, const ObsExt<NQ, NV>& x, unsigned f) {
     int k = 0;
 #pragma unroll
     for (int j = 0; j < PRE; ++j) dst[k++] = base[j];
@@ -89,18 +89,18 @@ struct StepResult {
 constexpr double REACH_RADIUS = 0.3;  // wrapper.py:203
 constexpr double REACH_BONUS = 5.0;   // wrapper.py:151-152
 
-__device__ __forceinline__ Pcg64 load_pcg(const uint64_t* p, int64_t i) {
+__host__ __device__ __forceinline__ Pcg64 load_pcg(const uint64_t* p, int64_t i) {
     const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p + 4 * i);
     ulonglong2 a = q[0], b = q[1];
     return Pcg64{a.x, a.y, b.x, b.y};
 }
-__device__ __forceinline__ void store_pcg(uint64_t* p, int64_t i, const Pcg64& g) {
+__host__ __device__ __forceinline__ void store_pcg(uint64_t* p, int64_t i, const Pcg64& g) {
     // the increment never changes
     *reinterpret_cast<ulonglong2*>(p + 4 * i) = make_ulonglong2(g.hi, g.lo);
 }
 
 // EnvWrapper.reset for one env.  full: re-place the robot (first reset, or goal not reached).
-__device__ inline void point_reset(PointHot& h, const EnvCold& cold, int64_t i, bool full) {
+__host__ __device__ inline void point_reset(PointHot& h, const EnvCold& cold, int64_t i, bool full) {
     if (full) {
         // Engine.reset() (wrapper.py:190) then PointEnv.set_pos -> Engine.reset() again
         // (wrapper.py:302): the heading that survives is the one drawn with _seed + 2.
@@ -135,7 +135,7 @@ constexpr int POINT_OBS_PRE = 3;
 
 // qpos / qvel are the joint coordinates (two slides in the robot body's frame, one hinge), relative to the body
 // pose PointEnv.set_pos wrote into the model (wrapper.py:301-305): the same view mr_env_get_state exports.
-__device__ inline void point_obs_ext(const PointHot& h, const EnvCold& cold, int64_t i, PointExt& x) {
+__host__ __device__ inline void point_obs_ext(const PointHot& h, const EnvCold& cold, int64_t i, PointExt& x) {
     x.ctrl[0] = h.cx; x.ctrl[1] = h.cz;
     x.goal_dist = (float)exp(-point::dist2((double)h.gx, (double)h.gy, h.d.px, h.d.py));
     const float2 b = cold.body_xy[i];
@@ -154,7 +154,7 @@ __device__ inline void point_obs_ext(const PointHot& h, const EnvCold& cold, int
 // One VecEnv step of one env.  obs receives the row the VecEnv returns (post-reset when
 // done); term_obs receives info["terminal_observation"] when done.  ext / term_ext (may be NULL): the optional keys
 // of the same two observations.
-__device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, int64_t i,
+__host__ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, int64_t i,
                                             float a0, float a1, const EnvCfg& cfg, float* obs,
                                             float* term_obs, PointExt* ext = nullptr, PointExt* term_ext = nullptr) {
     StepResult r;
@@ -167,14 +167,14 @@ __device__ inline StepResult point_env_step(PointHot& h, const EnvCold& cold, in
     const double dprev = point::dist2(gx, gy, prevx, prevy);
     const double dcur = point::dist2(gx, gy, h.d.px, h.d.py);
     r.reach = dcur < REACH_RADIUS;
-    double reward = __dsub_rn(dprev, dcur);
-    if (r.reach) reward = __dadd_rn(reward, REACH_BONUS);
+    double reward = rn::sub(dprev, dcur);
+    if (r.reach) reward = rn::add(reward, REACH_BONUS);
     h.elapsed += 1;
     const bool term = r.reach && cfg.terminate_on_goal;
     const bool tl = cfg.time_limit > 0 && h.elapsed >= cfg.time_limit;
     r.done = term || tl;
     r.trunc = tl && !term;
-    h.ep_ret = __dadd_rn(h.ep_ret, reward);
+    h.ep_ret = rn::add(h.ep_ret, reward);
     r.rew = (float)reward;
     r.ep_r = h.ep_ret;
     r.ep_l = h.elapsed;

@@ -223,7 +223,7 @@ __host__ __device__ __forceinline__ void substeps(const K& k, Dyn& d, double cx,
     c = u.c;
     s = u.s;
 }
-__device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
+__host__ __device__ __forceinline__ void substeps(Dyn& d, double cx, double cz) {
     double c, s;
     const K k = make_k();
     substeps(k, d, cx, cz, c, s);
@@ -261,7 +261,7 @@ __host__ __device__ __forceinline__ void sensors_cs(const K& k, const Dyn& d, do
     o[12] = (float)u2;
     o[13] = 0.f;
 }
-__device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
+__host__ __device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, float gx, float gy,
                                         float* o) {
     double s, c;
     sincos(d.psi, &s, &c);
@@ -272,9 +272,9 @@ __device__ __forceinline__ void sensors(const Dyn& d, double cx, double cz, floa
 
 // ||a - b|| exactly as numpy evaluates it on two-vectors (no contraction): the reached flag
 // and the reward must not depend on the compiler's FMA choices.
-__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
-    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
-    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+__host__ __device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
+    double dx = rn::sub(ax, bx), dy = rn::sub(ay, by);
+    return rn::root(rn::add(rn::mul(dx, dx), rn::mul(dy, dy)));
 }
 
 }  // namespace point
